@@ -1,0 +1,483 @@
+"""bench.py -- SEA attack throughput on B200 (BASELINE.json metric) + kernel roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One *step* = the full Segmentation Ensemble Attack on one batch: the three SEA losses
+(mask-ce-bal, mask-ce-avg, js-avg), each ``apgd_largereps`` with n_iter=10 (stages 3/3/4 at
+2eps/1.5eps/eps), on UperNet-ConvNeXt-T_CVST (random init), 150 classes, 16 synthetic 512x512
+images per GPU, eps=8/255 (BASELINE.json configs[1]), followed by the per-batch adversarial
+bookkeeping: argmax of the adversarial points, exact int64 per-image counters, (N>1: the one
+int64 all-reduce), worst-case aACC.  ``value`` = attacked image-iterations per second over all
+ranks with the batch resident in HBM; ``e2e`` = the same through the public API with the batch
+coming from pinned host memory and x_adv / acc going back to the host every step.
+
+``--impl reference`` times the CPU implementation of the same path on the box's host cores:
+the unmodified reference attacker when a copy travels under baseline/_ref, else the oracle port.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOSSES = ["mask-ce-bal", "mask-ce-avg", "js-avg"]
+METRIC = "SEA attacked image-iterations/sec (UperNet-ConvNeXt-T, 150 cls, 512x512)"
+UNIT = "image-iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--classes", type=int, default=150)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--n-iter", type=int, default=10)
+    ap.add_argument("--eps", type=float, default=8.0)
+    ap.add_argument("--variant", default="T")
+    ap.add_argument("--micro", action="store_true", help="config-5 kernel microbench instead of the SEA step")
+    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        top = sorted(sm)[len(sm) // 2:] if sm else []  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ ours
+def make_batch(B, C, S, seed, device=None, pin=False):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, S, S, generator=g)
+    y = torch.randint(0, C, (B, S, S), generator=g)
+    if pin:
+        return x.pin_memory(), y.pin_memory()
+    return x.to(device), y.to(device)
+
+
+_PINNED = {}
+
+
+def sea_step(mods, model, x, y, w, args, world, e2e_host=None):
+    """Full SEA on one batch + the per-batch bookkeeping.  Returns worst-case accuracy [B]."""
+    import torch
+
+    att, ops, dist_mod = mods["attacker"], mods["ops"], mods["dist"]
+    if e2e_host is not None:  # host buffers -> device inside the timed region
+        x = e2e_host[0].to(x.device, non_blocking=True)
+        y = e2e_host[1].to(y.device, non_blocking=True)
+    B, C = x.shape[0], args.classes
+    preds = []
+    x_advs = []
+    for loss in LOSSES:
+        x_adv, _, acc = att.apgd_largereps(
+            model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
+            track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C)
+        with torch.no_grad():
+            out = model(x_adv)
+        preds.append(ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred)
+        x_advs.append(x_adv)
+    cnt = ops.pixel_hist(torch.stack(preds).flatten(0, 1), y, C)
+    inter, tgt, prd = (cnt[k].view(len(LOSSES), B, C) for k in ("inter", "tgt", "prd"))
+    rank = int(os.environ.get("RANK", 0))
+    gi, gt, gp, _ = dist_mod.allreduce_counters(B * world, rank * B, inter, tgt, prd)
+    acc_an, worst = ops.sea_worst_acc(gi, gt)
+    if e2e_host is not None:  # results back to pinned host memory (tools/infer.py:151 keeps every x_adv)
+        if "out" not in _PINNED:
+            _PINNED["out"] = [torch.empty(xa.shape, dtype=xa.dtype).pin_memory() for xa in x_advs]
+            _PINNED["worst"] = torch.empty(worst.shape, dtype=worst.dtype).pin_memory()
+        for h, xa in zip(_PINNED["out"], x_advs):
+            h.copy_(xa, non_blocking=True)
+        _PINNED["worst"].copy_(worst, non_blocking=True)
+        return worst, (gi, gt, gp), _PINNED
+    return worst, (gi, gt, gp), None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.load_package()
+    from importlib import import_module
+
+    mods = {k: import_module("robseg_b200." + v) for k, v in dict(
+        attacker="semseg.attacker", ops="ops", dist="dist", lib="_lib", consumers="consumers",
+        worse="tools.worse_only").items()}
+    mods["lib"].load()  # fails loudly if the CUDA extension is missing
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.micro:
+        return run_micro(args, mods, dev, rank, world)
+
+    torch.manual_seed(0)
+    model = mods["consumers"].upernet_convnext(args.variant, args.classes).to(dev).eval()
+    for p in model.parameters():
+        p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
+    B, C, S = args.batch, args.classes, args.size
+    w = (0.5 + torch.rand(C, generator=torch.Generator().manual_seed(1))).to(dev)  # class-balance weights
+    x, y = make_batch(B, C, S, 100 + rank, dev)
+    hx, hy = make_batch(B, C, S, 100 + rank, pin=True)
+    iters_per_step = B * args.n_iter * len(LOSSES)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        keep = None
+        for _ in range(n_steps):
+            torch.manual_seed(1234)
+            worst, counters, host = sea_step(mods, model, x, y, w, args, world, (hx, hy) if e2e else None)
+            keep = (worst, counters, host)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), keep
+
+    for _ in range(args.warmup):
+        torch.manual_seed(1234)
+        sea_step(mods, model, x, y, w, args, world)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = mods["lib"].launches
+    mods["ops"].profile_start()
+    ms, keep = timed(args.steps, e2e=False)
+    prof = mods["ops"].profile_stop()
+    launches = mods["lib"].launches - launches0
+    ms_e2e, keep_e2e = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # epilogue (once per run, outside the steps): evalSEA's sequential greedy worst-case mIoU
+    t_ep = time.time()
+    gi, gt, gp = keep[1]
+    miou, _ = mods["worse"].greedy_worst_miou(gi.cpu().numpy(), (gt + gp - gi).cpu().numpy())
+    t_ep = (time.time() - t_ep) * 1e3
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * iters_per_step * args.steps / (ms / 1e3)
+    value_e2e = world * iters_per_step * args.steps / (ms_e2e / 1e3)
+    peaks = load_peaks()
+    by = {}
+    for name, nbytes, t in prof:
+        d = by.setdefault(name, [0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += t
+        d[2] += 1
+    lg = by.get("loss_grad", [0, 1e-9, 1])
+    achieved = lg[0] / (lg[1] / 1e3) / 1e9
+    ours_ms = sum(v[1] for v in by.values())
+    h2d = B * 3 * S * S * 4 + B * S * S * 8
+    d2h = len(LOSSES) * B * 3 * S * S * 4 + B * world * 4
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"configs[1]: full SEA (mask-ce-bal, mask-ce-avg, js-avg) x apgd_largereps n_iter={args.n_iter} "
+                        f"(3/3/4 @ 2eps/1.5eps/eps), UperNet-ConvNeXt-{args.variant}_CVST random init, "
+                        f"{C} classes, {S}x{S}, batch {B} per GPU, eps {args.eps:g}/255",
+            "image_iterations_per_step": iters_per_step * world,
+            "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + 1), "model_bwd_per_step": len(LOSSES) * args.n_iter,
+            "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)",
+            "l2_note": "inputs larger than L2: logits/dlogits 2x%.2f GB per launch" % (B * C * S * S * 4 / 1e9),
+            "parallelism": f"image-sharded dp{world}, one int64 all-reduce per step",
+            "epilogue": "evalSEA greedy worst-case mIoU once per run outside the steps: %.1f ms (mIoU %.4f)" % (t_ep, miou),
+            "attack_side_ms_per_step": round(ours_ms / args.steps, 3),
+            "attack_side_frac_of_step": round(ours_ms / ms, 4),
+            "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in by.items()},
+        },
+        "clocks": clocks,
+        "e2e": {"value": round(value_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,1> (fused loss+dlogits, C=%d)" % C,
+                     "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s",
+                     "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C),
+                     "peak_source": peaks[1], "launches_timed": lg[2],
+                     "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
+                     "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(key):
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------ microbench
+def run_micro(args, mods, dev, rank, world):
+    """BASELINE config 5: loss+dlogits, APGD step and histogram kernels alone at
+    [micro_batch,150,512,512]; one JSON line with per-kernel GB/s vs the HBM roofline."""
+    import torch
+
+    ops = mods["ops"]
+    B, C, S = args.micro_batch, args.classes, args.size
+    dt = torch.float32 if args.micro_dtype == "fp32" else torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(rank)
+    z = (3 * torch.randn(B, C, S, S, device=dev, generator=g)).to(dt)
+    y = torch.randint(0, C, (B, S, S), device=dev, generator=g)
+    y = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.5, z.argmax(1), y)
+    w = 0.5 + torch.rand(C, device=dev, generator=g)
+    dbuf = torch.empty_like(z)
+    x = torch.rand(B, 3, S, S, device=dev, generator=g)
+    xa, xo, gr, xn = (torch.rand_like(x) for _ in range(4))
+    step = torch.full((B,), 16 / 255, device=dev)
+    peaks = load_peaks()
+    res = {}
+
+    def time_it(name, fn, nbytes):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(max(args.steps, 5)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = statistics.median(ts)
+        res[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peaks[0], 4),
+                     "bytes": nbytes}
+
+    es = z.element_size()
+    for kind in LOSSES + ["ce-avg"]:
+        time_it("loss_grad/" + kind, lambda: ops.loss_fwd_bwd(z, y, kind, w, dlogits_out=dbuf),
+                2 * z.numel() * es + 8 * y.numel())
+    time_it("loss_only/mask-ce-avg", lambda: ops.loss_fwd_bwd(z, y, "mask-ce-avg", w, want_grad=False),
+            z.numel() * es + 8 * y.numel())
+    time_it("argmax", lambda: ops.loss_fwd_bwd(z, y, "argmax", want_grad=False, want_pred=True, want_stats=False),
+            z.numel() * es + 16 * y.numel())
+    time_it("apgd_step", lambda: ops.apgd_step(x, xa, xo, gr, step, 8 / 255, 0.75, xn), 20 * x.numel())
+    pred = z.argmax(1)
+    time_it("pixel_hist/counts", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel())
+    time_it("pixel_hist/full", lambda: ops.pixel_hist(pred, y, C, want_hist=True, want_counts=False), 16 * y.numel())
+    # the stock ATen chain of the reference on the same device (SURVEY 8d "also report")
+    if args.micro_dtype == "fp32" and B <= 16:
+        import torch.nn.functional as F
+
+        def aten_maskce():
+            zz = z.detach().requires_grad_()
+            mask = (zz.max(1)[1] == y) * (y != -1)
+            l = (mask.float().detach() * F.cross_entropy(zz, y, reduction="none", ignore_index=-1))
+            torch.autograd.grad(l.view(B, -1).mean(-1).sum(), [zz])
+
+        time_it("aten_chain/mask-ce-avg", aten_maskce, 2 * z.numel() * es + 8 * y.numel())
+    if rank == 0:
+        k = res["loss_grad/mask-ce-avg"]
+        print(json.dumps({
+            "metric": "attack-kernel microbench (loss+dlogits GB/s)", "value": k["GBps"], "unit": "GB/s",
+            "n_gpus": world, "steps": max(args.steps, 5), "warmup": max(args.warmup, 3), "ms_per_step": k["ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.micro_dtype,
+            "data": "synthetic", "config": {"workload": f"configs[4]: logits {B}x{C}x{S}x{S} {args.micro_dtype}",
+                                            "kernels": res, "l2_note": "inputs larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": k["GBps"], "peak": peaks[0], "unit": "GB/s", "frac": k["frac"],
+                         "traffic": load_traffic("micro_c%d_%s" % (C, args.micro_dtype)), "peak_source": peaks[1]},
+        }), flush=True)
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def _cpu_sample(args, loss, seed, prefer_reference=True):
+    """One bounded CPU sample of the same workload: apgd_largereps (n_iter=3 -> stages 0/0/3, each
+    stage still pays its initial forward+backward) on ONE 512x512 image, C classes, UperNet-
+    ConvNeXt-T on the host cores.  Returns (seconds, image_iterations, kind)."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    C, S, n_iter, B = args.classes, args.size, 3, 1
+    x, y = make_batch(B, C, S, seed)
+    w = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(1))
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if prefer_reference and os.path.isdir(os.path.join(ref_dir, "semseg")):
+        try:
+            import ref_shims
+
+            ref_shims.install()
+            if ref_dir not in sys.path:
+                sys.path.insert(0, ref_dir)
+            cwd = os.getcwd()
+            os.chdir(ref_dir)
+            try:
+                import semseg.attacker as RA
+                from semseg.models import UperNetForSemanticSegmentation
+            finally:
+                os.chdir(cwd)
+            key = ("ref", C)
+            if key not in _CPU_MODELS:
+                torch.manual_seed(0)
+                _CPU_MODELS[key] = UperNetForSemanticSegmentation("ConvNeXt-T_CVST", C, None).eval()
+            model = _CPU_MODELS[key]
+            t0 = time.time()
+            RA.apgd_largereps(model, x.clone(), y, w, norm="Linf", eps=args.eps / 255.0, n_iter=n_iter, loss=loss,
+                              track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C)
+            return time.time() - t0, B * n_iter, "reference"
+        except Exception as e:  # fall through to the oracle port
+            print(f"[bench] reference copy unusable ({e!r}); using the oracle port", file=sys.stderr)
+    import __graft_entry__ as ge
+    import robseg_oracle as O
+
+    ge.load_package()
+    from importlib import import_module
+
+    key = ("port", C)
+    if key not in _CPU_MODELS:
+        torch.manual_seed(0)
+        _CPU_MODELS[key] = import_module("robseg_b200.consumers").upernet_convnext(args.variant, C).eval()
+    model = O.TorchModelAdapter(_CPU_MODELS[key])
+    noise = [(2 * torch.rand_like(x) - 1).numpy() for _ in range(3)]
+    t0 = time.time()
+    O.apgd_largereps(model, x.numpy(), y.numpy(), w.numpy(), eps=args.eps / 255.0, n_iter=n_iter, loss=loss,
+                     early_stop=True, use_rs=True, rand_ts=noise)
+    _ = np
+    return time.time() - t0, B * n_iter, "port"
+
+
+_CPU_MODELS = {}
+
+
+def cpu_baseline(args, budget_s=25.0):
+    import torch
+
+    t, n, kind = 0.0, 0, None
+    for i, loss in enumerate(LOSSES):
+        dt, it, kind = _cpu_sample(args, loss, 100 + i)
+        t += dt
+        n += it
+        if t > budget_s:
+            break
+    return {"value": round(n / t, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "host_cpus": os.cpu_count(),
+            "sample": f"{i + 1} of the 3 SEA losses x apgd_largereps(n_iter=3 -> 0/0/3 + 3 stage inits) on 1 image "
+                      f"{args.size}x{args.size}, {args.classes} classes, UperNet-ConvNeXt-T on host cores, {t:.1f} s"}
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    for i in range(args.warmup):
+        _cpu_sample(args, LOSSES[i % 3], 50 + i)
+    t, n, kind = 0.0, 0, None
+    for i in range(args.steps):
+        dt, it, kind = _cpu_sample(args, LOSSES[i % 3], 100 + i)
+        t += dt
+        n += it
+    value = n / t
+    sample = (f"each step = one SEA loss (rotating {LOSSES}) x apgd_largereps(n_iter=3 -> stages 0/0/3, 6 fwd + 5 bwd) "
+              f"on 1 image {args.size}x{args.size}, {args.classes} classes, UperNet-ConvNeXt-T, host cores")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / max(args.steps, 1) * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1] on the host CPU, bounded sample: {sample}"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                         "host_cpus": os.cpu_count(), "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

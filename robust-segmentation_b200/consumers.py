@@ -1,0 +1,131 @@
+"""Plain-PyTorch segmentation networks used as the *consumer* around the hot path in
+``bench.py`` and the GPU tests.  NOT part of the accelerated path and not a rebuild of the
+reference's model zoo (out of scope): the attack only needs
+``model(x) -> logits [B,C,H,W]`` at input resolution and autograd back to ``x``; these run on
+stock cuDNN / cuBLAS.
+
+``upernet_convnext(variant, n_cls)`` builds the architecture BASELINE.json's configs name
+(UperNet decode head over ConvNeXt-T/S with the two-conv "CvSt" stem, bilinear up-sampling of
+the logits to the input size), random-initialised -- there is no network for checkpoints.
+Shapes follow the published ConvNeXt / UperNet designs (depths 3-3-9-3 or 3-3-27-3, widths
+96-192-384-768, PSP pool scales 1-2-3-6, 512 decoder channels, 256-channel FCN aux head).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+CONVNEXT = {"T": (3, 3, 9, 3), "S": (3, 3, 27, 3)}
+WIDTHS = (96, 192, 384, 768)
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """LayerNorm over the channel axis of an NCHW tensor."""
+
+    def forward(self, x):
+        return F.layer_norm(x.permute(0, 2, 3, 1), self.normalized_shape, self.weight, self.bias,
+                            self.eps).permute(0, 3, 1, 2)
+
+
+class NeXtBlock(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dw = nn.Conv2d(dim, dim, 7, padding=3, groups=dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+        self.scale = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        y = self.dw(x).permute(0, 2, 3, 1)
+        y = self.fc2(F.gelu(self.fc1(self.norm(y)))) * self.scale
+        return x + y.permute(0, 3, 1, 2)
+
+
+class ConvNeXtCvSt(nn.Module):
+    def __init__(self, depths):
+        super().__init__()
+        w = WIDTHS
+        stem = nn.Sequential(nn.Conv2d(3, w[0] // 2, 3, 2, 1), LayerNorm2d(w[0] // 2, eps=1e-6), nn.GELU(),
+                             nn.Conv2d(w[0] // 2, w[0], 3, 2, 1), LayerNorm2d(w[0], eps=1e-6), nn.GELU())
+        self.down = nn.ModuleList([stem] + [
+            nn.Sequential(LayerNorm2d(w[i], eps=1e-6), nn.Conv2d(w[i], w[i + 1], 2, 2)) for i in range(3)])
+        self.stages = nn.ModuleList([nn.Sequential(*[NeXtBlock(w[i]) for _ in range(d)])
+                                     for i, d in enumerate(depths)])
+        self.out_norm = nn.ModuleList([LayerNorm2d(c, eps=1e-6) for c in w])
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        feats = []
+        for d, s, n in zip(self.down, self.stages, self.out_norm):
+            x = s(d(x))
+            feats.append(n(x))
+        return feats
+
+
+def conv_bn_relu(cin, cout, k):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, padding=k // 2, bias=False), nn.BatchNorm2d(cout), nn.ReLU())
+
+
+class UperHead(nn.Module):
+    def __init__(self, n_cls, ch=512, scales=(1, 2, 3, 6)):
+        super().__init__()
+        w = WIDTHS
+        self.psp = nn.ModuleList([nn.Sequential(nn.AdaptiveAvgPool2d(s), conv_bn_relu(w[-1], ch, 1)) for s in scales])
+        self.bottleneck = conv_bn_relu(w[-1] + len(scales) * ch, ch, 3)
+        self.lateral = nn.ModuleList([conv_bn_relu(c, ch, 1) for c in w[:-1]])
+        self.fpn = nn.ModuleList([conv_bn_relu(ch, ch, 3) for _ in w[:-1]])
+        self.fuse = conv_bn_relu(len(w) * ch, ch, 3)
+        self.classifier = nn.Conv2d(ch, n_cls, 1)
+
+    def forward(self, feats):
+        top = feats[-1]
+        size = top.shape[2:]
+        pooled = [top] + [F.interpolate(p(top), size=size, mode="bilinear", align_corners=False) for p in self.psp]
+        lat = [l(f) for l, f in zip(self.lateral, feats)] + [self.bottleneck(torch.cat(pooled, 1))]
+        for i in range(len(lat) - 1, 0, -1):
+            lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="bilinear",
+                                                    align_corners=False)
+        outs = [f(l) for f, l in zip(self.fpn, lat)] + [lat[-1]]
+        size0 = outs[0].shape[2:]
+        outs = [outs[0]] + [F.interpolate(o, size=size0, mode="bilinear", align_corners=False) for o in outs[1:]]
+        return self.classifier(self.fuse(torch.cat(outs, 1)))
+
+
+class UperNetConvNeXt(nn.Module):
+    def __init__(self, variant="T", n_cls=150):
+        super().__init__()
+        self.backbone = ConvNeXtCvSt(CONVNEXT[variant])
+        self.decode_head = UperHead(n_cls)
+        self.aux_head = nn.Sequential(conv_bn_relu(WIDTHS[2], 256, 3), nn.Conv2d(256, n_cls, 1))
+
+    def forward(self, x, lbl=None):
+        feats = self.backbone(x)
+        logits = F.interpolate(self.decode_head(feats), size=x.shape[2:], mode="bilinear", align_corners=False)
+        if lbl is None:
+            return logits
+        aux = F.interpolate(self.aux_head(feats[2]), size=x.shape[2:], mode="bilinear", align_corners=False)
+        loss = F.cross_entropy(logits, lbl, ignore_index=-1) + 0.4 * F.cross_entropy(aux, lbl, ignore_index=-1)
+        return (loss, logits) if self.training else logits
+
+
+def upernet_convnext(variant="T", n_cls=150):
+    return UperNetConvNeXt(variant, n_cls)
+
+
+class TinySegNet(nn.Module):
+    """3 -> hidden -> C two-conv net for smoke tests (milliseconds on any device)."""
+
+    def __init__(self, n_cls=21, hidden=8, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.c1 = nn.Conv2d(3, hidden, 3, padding=1)
+        self.c2 = nn.Conv2d(hidden, n_cls, 3, padding=1)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * (0.6 if p.dim() > 1 else 0.1))
+
+    def forward(self, x):
+        return self.c2(torch.tanh(self.c1(x - 0.5)))

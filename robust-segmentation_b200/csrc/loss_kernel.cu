@@ -1,0 +1,630 @@
+// Fused per-pixel softmax + {CE, Mask-CE, Mask-CE-balanced, JS} loss + d(loss)/d(logits)
+// + argmax + per-image partial sums, one read of the logits and one write of the gradient.
+//
+// Replaces the ATen chains of semseg/attacker.py:143-173,187-240,251-257 and the autograd
+// of their per-image mean (formulas in section 10).
+//
+// Data layout.  Logits are NCHW: the softmax axis (C) has stride HW, pixels are contiguous.
+// A *warp tile* is [C channels x 32*VEC pixels]; every lane owns VEC adjacent pixels and
+// walks the channel axis, so each shared-memory row access is one conflict-free 128*VEC/…
+// byte wavefront and every global store is a full coalesced line.
+//
+// Fast path (loss_tma_kernel): persistent CTAs, one per SM.  Warp 0 is a TMA producer: one
+// elected lane streams warp tiles into a ring of shared-memory stages with 3-D tensor-map
+// bulk copies (cp.async.bulk.tensor, SASS UTMALDG) over the [B][C][HW] view, box
+// {32*VEC, C, 1}; completion is signalled on a per-stage "full" mbarrier.  Warps 1..W are
+// consumers: each takes every W-th ring item, makes three passes over ITS OWN stage
+// (max/argmax, sum-exp, gradient), writes the gradient straight from registers and releases
+// the stage through the "empty" mbarrier.  No __syncthreads in the steady state.
+//
+// Generic path (loss_generic_kernel): any HW / alignment / C; each warp loads its tile with
+// plain coalesced loads into a private stage and runs the same per-tile code.
+//
+// Determinism: per-tile partial sums are written to a workspace and reduced per image in a
+// fixed order by loss_finalize_kernel (no float atomics), so repeated runs are bit-identical.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace robseg {
+
+struct LossParams {
+  const void* logits;
+  const int64_t* labels;
+  const float* class_w;
+  const float* grad_scale;
+  const float* upstream;
+  void* dlogits;
+  float* loss_pix;
+  int64_t* pred;
+  float4* partials;
+  int64_t HW;
+  int kind, ignore_index, B, C;
+  int tiles_per_img, num_tiles, n_stages, n_consumers;
+  float inv_hw;
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ---- element access ------------------------------------------------------------------------
+template <typename T, int VEC>
+struct Vec;
+
+template <int VEC>
+struct Vec<float, VEC> {
+  static __device__ __forceinline__ void lds(const float* p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+      v[0] = *p;
+    } else if constexpr (VEC == 2) {
+      float2 t = *reinterpret_cast<const float2*>(p);
+      v[0] = t.x, v[1] = t.y;
+    } else {
+      static_assert(VEC == 4, "fp32 VEC in {1,2,4}");
+      float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+  }
+  static __device__ __forceinline__ void stg(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+      __stcs(p, v[0]);
+    } else if constexpr (VEC == 2) {
+      __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    } else {
+      __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+  static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+  static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+};
+
+template <int VEC>
+struct Vec<__nv_bfloat16, VEC> {
+  using T = __nv_bfloat16;
+  static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  static __device__ __forceinline__ void lds(const T* p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+      v[0] = __bfloat162float(*p);
+    } else if constexpr (VEC == 2) {
+      unpack(*reinterpret_cast<const uint32_t*>(p), v[0], v[1]);
+    } else if constexpr (VEC == 4) {
+      uint2 t = *reinterpret_cast<const uint2*>(p);
+      unpack(t.x, v[0], v[1]), unpack(t.y, v[2], v[3]);
+    } else {
+      static_assert(VEC == 8, "bf16 VEC in {1,2,4,8}");
+      uint4 t = *reinterpret_cast<const uint4*>(p);
+      unpack(t.x, v[0], v[1]), unpack(t.y, v[2], v[3]);
+      unpack(t.z, v[4], v[5]), unpack(t.w, v[6], v[7]);
+    }
+  }
+  static __device__ __forceinline__ void stg(T* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+      *p = __float2bfloat16_rn(v[0]);
+    } else if constexpr (VEC == 2) {
+      __stcs(reinterpret_cast<uint32_t*>(p), pack(v[0], v[1]));
+    } else if constexpr (VEC == 4) {
+      __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack(v[0], v[1]), pack(v[2], v[3])));
+    } else {
+      __stcs(reinterpret_cast<uint4*>(p), make_uint4(pack(v[0], v[1]), pack(v[2], v[3]),
+                                                      pack(v[4], v[5]), pack(v[6], v[7])));
+    }
+  }
+  static __device__ __forceinline__ float ld1(const T* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st1(T* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---- one warp tile -------------------------------------------------------------------------
+// tile: shared memory [C][32*VEC] of T, already filled (zeros beyond HW).
+template <typename T, int VEC>
+__device__ __forceinline__ void process_tile(const LossParams& p, const T* __restrict__ tile,
+                                             int tile_idx, int lane) {
+  constexpr int ROW = 32 * VEC;
+  constexpr int NACC = (VEC >= 4) ? 1 : 4 / VEC;  // independent accumulator sets per pixel
+  constexpr int UNR = 8;
+  using V = Vec<T, VEC>;
+  const int C = p.C;
+  const int b = tile_idx / p.tiles_per_img;
+  const int64_t px = (int64_t)(tile_idx - b * p.tiles_per_img) * ROW + lane * VEC;
+  const bool inb = px < p.HW;  // HW % VEC == 0 on the vector path, so a lane is all in or out
+  const int64_t pix = (int64_t)b * p.HW + px;
+  const T* col = tile + lane * VEC;
+
+  // labels: issued now, consumed after pass 1
+  int y[VEC];
+  if (inb) {
+    if constexpr (VEC == 1) {
+      y[0] = (int)__ldg(p.labels + pix);
+    } else {
+      const longlong2* lp = reinterpret_cast<const longlong2*>(p.labels + pix);
+#pragma unroll
+      for (int j = 0; j < VEC / 2; ++j) {
+        longlong2 t = __ldg(lp + j);
+        y[2 * j] = (int)t.x, y[2 * j + 1] = (int)t.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) y[j] = p.ignore_index;
+  }
+
+  // ---- pass 1: max and argmax (lowest index on ties, as Tensor.max(1)) -------------------
+  float m[NACC][VEC];
+  int am[NACC][VEC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[a][j] = -INFINITY, am[a][j] = 0;
+  int c = 0;
+#pragma unroll 1
+  for (; c + UNR <= C; c += UNR) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float v[VEC];
+      V::lds(col + (c + u) * ROW, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const bool g = v[j] > m[u % NACC][j];
+        m[u % NACC][j] = g ? v[j] : m[u % NACC][j];
+        am[u % NACC][j] = g ? (c + u) : am[u % NACC][j];
+      }
+    }
+  }
+#pragma unroll 1
+  for (; c < C; ++c) {
+    float v[VEC];
+    V::lds(col + c * ROW, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      // the tail always follows full groups, so set 0 still sees ascending indices
+      const bool g = v[j] > m[0][j] || (v[j] == m[0][j] && c < am[0][j]);
+      m[0][j] = g ? v[j] : m[0][j];
+      am[0][j] = g ? c : am[0][j];
+    }
+  }
+  float mx[VEC];
+  int amx[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    mx[j] = m[0][j], amx[j] = am[0][j];
+#pragma unroll
+    for (int a = 1; a < NACC; ++a) {
+      const bool g = m[a][j] > mx[j] || (m[a][j] == mx[j] && am[a][j] < amx[j]);
+      mx[j] = g ? m[a][j] : mx[j];
+      amx[j] = g ? am[a][j] : amx[j];
+    }
+  }
+
+  bool valid[VEC], hit[VEC];
+  int ys[VEC];
+  int n_correct = 0, n_valid = 0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+    hit[j] = valid[j] && (amx[j] == y[j]);
+    ys[j] = valid[j] ? y[j] : 0;
+    n_correct += hit[j];
+    n_valid += valid[j];
+  }
+  if (p.pred != nullptr && inb) {
+    if constexpr (VEC == 1) {
+      p.pred[pix] = amx[0];
+    } else {
+      longlong2* pp = reinterpret_cast<longlong2*>(p.pred + pix);
+#pragma unroll
+      for (int j = 0; j < VEC / 2; ++j) pp[j] = make_longlong2(amx[2 * j], amx[2 * j + 1]);
+    }
+  }
+
+  float loss_sum = 0.f, ce_sum = 0.f;
+  if (p.kind != ROBSEG_LOSS_ARGMAX) {
+    // ---- pass 2: sum of exp(z - max) ------------------------------------------------------
+    // exp(z-m) = 2^(z*log2e - mL) with mL = fl(m*log2e); the rounding residual of that
+    // product is common to all channels (cancels in softmax) and is removed from the
+    // log-sum-exp exactly through `resid`.
+    float mL[VEC], resid[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      mL[j] = mx[j] * kLog2e;
+      resid[j] = fmaf(mx[j], kLog2e, -mL[j]);
+    }
+    float s[NACC][VEC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[a][j] = 0.f;
+    c = 0;
+#pragma unroll 1
+    for (; c + UNR <= C; c += UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float v[VEC];
+        V::lds(col + (c + u) * ROW, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s[u % NACC][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+      }
+    }
+#pragma unroll 1
+    for (; c < C; ++c) {
+      float v[VEC];
+      V::lds(col + c * ROW, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+    }
+
+    // ---- per-pixel loss terms ---------------------------------------------------------------
+    float kfac[VEC], sub[VEC], ey[VEC], loss[VEC];
+    const float g_img = p.grad_scale ? __ldg(p.grad_scale + b) : p.inv_hw;
+    bool any_grad = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float st = s[0][j];
+#pragma unroll
+      for (int a = 1; a < NACC; ++a) st += s[a][j];
+      const float zy = V::ld1(col + ys[j] * ROW + j);
+      const float ln_s = logf(st) - resid[j] * kLn2;  // lse - m
+      const float logp = (zy - mx[j]) - ln_s;          // log softmax_y  (<= 0)
+      const float ce = valid[j] ? -logp : 0.f;
+      float l, coef;
+      if (p.kind == ROBSEG_LOSS_CE) {
+        l = ce, coef = valid[j] ? 1.f : 0.f;
+      } else if (p.kind == ROBSEG_LOSS_MASK_CE) {
+        l = hit[j] ? ce : 0.f, coef = hit[j] ? 1.f : 0.f;
+      } else if (p.kind == ROBSEG_LOSS_MASK_CE_BAL) {
+        const float w = (p.class_w != nullptr) ? __ldg(p.class_w + ys[j]) : 1.f;
+        l = hit[j] ? w * ce : 0.f, coef = hit[j] ? w : 0.f;
+      } else {  // JS(softmax || one-hot), SURVEY section 10
+        const float py = expf(logp);
+        const float l1p = log1pf(py);
+        l = valid[j] ? 0.5f * (2.f * kLn2 + py * logp - (1.f + py) * l1p) : 0.f;
+        coef = valid[j] ? -0.5f * py * (logp - l1p) : 0.f;
+      }
+      loss[j] = l;
+      loss_sum += l;
+      ce_sum += ce;
+      float gs = g_img;
+      if (p.upstream != nullptr && inb) gs *= __ldg(p.upstream + pix + j);
+      const float cg = coef * gs;
+      kfac[j] = cg / st;
+      sub[j] = cg;
+      ey[j] = ex2_approx(fmaf(zy, kLog2e, -mL[j]));
+      any_grad |= (cg != 0.f);
+    }
+    if (p.loss_pix != nullptr && inb) {
+      if constexpr (VEC == 1) {
+        p.loss_pix[pix] = loss[0];
+      } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(p.loss_pix + pix) = make_float2(loss[0], loss[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC / 4; ++j)
+          reinterpret_cast<float4*>(p.loss_pix + pix)[j] =
+              make_float4(loss[4 * j], loss[4 * j + 1], loss[4 * j + 2], loss[4 * j + 3]);
+      }
+    }
+
+    // ---- pass 3: gradient, written straight from registers ---------------------------------
+    if (p.dlogits != nullptr) {
+      T* gout = reinterpret_cast<T*>(p.dlogits) + (int64_t)b * C * p.HW + px;
+      const bool warp_any = __any_sync(0xffffffffu, any_grad);
+      if (!warp_any) {
+        // every pixel of the tile is masked out (wrongly classified / ignored): zeros
+        float zero[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) zero[j] = 0.f;
+        if (inb) {
+#pragma unroll 4
+          for (c = 0; c < C; ++c) V::stg(gout + (int64_t)c * p.HW, zero);
+        }
+      } else {
+        c = 0;
+#pragma unroll 1
+        for (; c + UNR <= C; c += UNR) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            float v[VEC], g[VEC];
+            V::lds(col + (c + u) * ROW, v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+              g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
+            if (inb) V::stg(gout + (int64_t)(c + u) * p.HW, g);
+          }
+        }
+#pragma unroll 1
+        for (; c < C; ++c) {
+          float v[VEC], g[VEC];
+          V::lds(col + c * ROW, v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
+          if (inb) V::stg(gout + (int64_t)c * p.HW, g);
+        }
+        // the label channel: coef*(p_y - 1).  Same thread, same address, program order.
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (sub[j] != 0.f)
+            V::st1(gout + (int64_t)ys[j] * p.HW + j, fmaf(ey[j], kfac[j], -sub[j]));
+      }
+    }
+  }
+
+  // ---- per-tile partials (fixed shuffle order -> deterministic) ----------------------------
+  loss_sum = warp_sum(loss_sum);
+  ce_sum = warp_sum(ce_sum);
+  n_correct = warp_sum(n_correct);
+  n_valid = warp_sum(n_valid);
+  if (lane == 0)
+    p.partials[tile_idx] =
+        make_float4(loss_sum, ce_sum, __int_as_float(n_correct), __int_as_float(n_valid));
+}
+
+// ---- fast path: persistent TMA ring --------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(512, 1)
+    loss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const LossParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                             ~static_cast<uintptr_t>(127));
+  constexpr int ROW = 32 * VEC;
+  const int S = p.n_stages, W = p.n_consumers;
+  const uint32_t stage_bytes = (uint32_t)p.C * ROW * sizeof(T);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* empty = full + S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < S; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int s = 0;
+      uint32_t round = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(empty + s, (round & 1u) ^ 1u);
+        mbar_arrive_expect_tx(full + s, stage_bytes);
+        const int b = tile / p.tiles_per_img;
+        const int px0 = (tile - b * p.tiles_per_img) * ROW;
+        tma_load_3d(smem + (size_t)s * stage_bytes, &tmap, px0, 0, b, full + s);
+        if (++s == S) s = 0, ++round;
+      }
+    }
+  } else {  // ===== consumers: ring item `it` -> warp (it % W) =====
+    const int w = warp - 1;
+    int it = w;
+    int s = w % S;
+    uint32_t round = w / S;
+    for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles; tile += W * gridDim.x) {
+      mbar_wait(full + s, round & 1u);
+      process_tile<T, VEC>(p, reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes), tile,
+                           lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+      it += W;
+      s += W;
+      while (s >= S) s -= S, ++round;
+    }
+    (void)it;
+  }
+}
+
+// ---- generic path: any shape / alignment ---------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * p.C * 32;
+  const T* logits = reinterpret_cast<const T*>(p.logits);
+  for (int tile = blockIdx.x * W + warp; tile < p.num_tiles; tile += gridDim.x * W) {
+    const int b = tile / p.tiles_per_img;
+    const int64_t px = (int64_t)(tile - b * p.tiles_per_img) * 32 + lane;
+    const bool inb = px < p.HW;
+    const T* src = logits + (int64_t)b * p.C * p.HW + px;
+#pragma unroll 8
+    for (int c = 0; c < p.C; ++c)
+      stage[c * 32 + lane] = inb ? src[(int64_t)c * p.HW] : T(0.f);
+    __syncwarp();
+    process_tile<T, 1>(p, stage, tile, lane);
+    __syncwarp();
+  }
+}
+
+// ---- fixed-order per-image reduction of the tile partials ----------------------------------
+__global__ void __launch_bounds__(256)
+    loss_finalize_kernel(const float4* __restrict__ partials, int tiles_per_img,
+                         const float* __restrict__ grad_scale, double inv_hw, float* loss_img,
+                         float* track_img, int32_t* correct_img, int32_t* valid_img) {
+  __shared__ double sh_l[256], sh_c[256];
+  __shared__ int sh_k[256], sh_v[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  double l = 0.0, ce = 0.0;
+  int k = 0, v = 0;
+  const float4* src = partials + (size_t)b * tiles_per_img;
+  for (int i = t; i < tiles_per_img; i += 256) {
+    const float4 q = src[i];
+    l += (double)q.x, ce += (double)q.y, k += __float_as_int(q.z), v += __float_as_int(q.w);
+  }
+  sh_l[t] = l, sh_c[t] = ce, sh_k[t] = k, sh_v[t] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) sh_l[t] += sh_l[t + o], sh_c[t] += sh_c[t + o], sh_k[t] += sh_k[t + o], sh_v[t] += sh_v[t + o];
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double g = grad_scale ? (double)grad_scale[b] : inv_hw;
+    if (loss_img) loss_img[b] = (float)(g * sh_l[0]);
+    if (track_img) track_img[b] = (float)(sh_c[0] * inv_hw);
+    if (correct_img) correct_img[b] = sh_k[0];
+    if (valid_img) valid_img[b] = sh_v[0];
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // ring + barriers + alignment slack
+
+static int pick_vec(int C, int esize) {
+  // widest per-lane vector whose stage ([C][32*VEC] elements) stays <= ~24 KB, so the ring
+  // keeps >= 8 stages; per-lane bytes are capped at 16.
+  const int max_vec = 16 / esize;
+  int vec = max_vec;
+  while (vec > (esize == 2 ? 2 : 1) && (size_t)C * 32 * vec * esize > 24 * 1024) vec >>= 1;
+  return vec;
+}
+
+template <typename T, int VEC>
+static int launch_tma(const LossParams& p0, cudaStream_t stream) {
+  LossParams p = p0;
+  constexpr int ROW = 32 * VEC;
+  p.tiles_per_img = (int)((p.HW + ROW - 1) / ROW);
+  p.num_tiles = p.B * p.tiles_per_img;
+  const size_t stage = (size_t)p.C * ROW * sizeof(T);
+  int S = (int)((kSmemBudget - 512) / stage);
+  if (S > 32) S = 32;
+  int W = S - (S >= 8 ? S / 4 : 1);
+  if (W > 15) W = 15;
+  if (W < 1) W = 1;
+  p.n_stages = S, p.n_consumers = W;
+  const size_t smem = S * stage + 2 * S * sizeof(uint64_t) + 128;
+
+  CUtensorMap tmap;
+  const cuuint64_t dims[3] = {(cuuint64_t)p.HW, (cuuint64_t)p.C, (cuuint64_t)p.B};
+  const cuuint64_t strides[2] = {(cuuint64_t)p.HW * sizeof(T), (cuuint64_t)p.HW * p.C * sizeof(T)};
+  const cuuint32_t box[3] = {(cuuint32_t)ROW, (cuuint32_t)p.C, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  auto encode = get_encode();
+  ROBSEG_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  CUresult r = encode(&tmap,
+                      sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      3, const_cast<void*>(p.logits), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ROBSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+
+  auto kern = loss_tma_kernel<T, VEC>;
+  ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sm_count();
+  const int max_useful = (p.num_tiles + W - 1) / W;
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+  kern<<<grid, 32 * (W + 1), smem, stream>>>(tmap, p);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int launch_generic(const LossParams& p0, cudaStream_t stream) {
+  LossParams p = p0;
+  p.tiles_per_img = (int)((p.HW + 31) / 32);
+  p.num_tiles = p.B * p.tiles_per_img;
+  const size_t stage = (size_t)p.C * 32 * sizeof(T);
+  ROBSEG_REQUIRE(stage <= kSmemBudget, "C=%d too large for one shared-memory stage", p.C);
+  int W = (int)(kSmemBudget / 2 / stage);  // aim for two CTAs per SM
+  if (W > 8) W = 8;
+  if (W < 1) W = 1;
+  const size_t smem = W * stage;
+  auto kern = loss_generic_kernel<T>;
+  ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sm_count() * 2;
+  const int max_useful = (p.num_tiles + W - 1) / W;
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+  kern<<<grid, 32 * W, smem, stream>>>(p);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int tiles_upper_bound(int B, int64_t HW) { return B * (int)((HW + 31) / 32); }
+
+}  // namespace robseg
+
+using namespace robseg;
+
+extern "C" size_t robseg_loss_workspace_bytes(int B, int C, int64_t HW, int dtype) {
+  (void)C, (void)dtype;
+  if (B <= 0 || HW <= 0) return 0;
+  return (size_t)tiles_upper_bound(B, HW) * sizeof(float4);
+}
+
+extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t* labels,
+                                   const float* class_w, int loss_kind, int ignore_index, int B,
+                                   int C, int64_t HW, const float* grad_scale,
+                                   const float* upstream_pix, void* dlogits, float* loss_pix,
+                                   int64_t* pred, float* loss_img, float* track_img,
+                                   int32_t* correct_img, int32_t* valid_img, void* workspace,
+                                   size_t workspace_bytes, robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(logits && labels, "logits/labels must not be NULL");
+  ROBSEG_REQUIRE(dtype == ROBSEG_F32 || dtype == ROBSEG_BF16, "unsupported dtype %d", dtype);
+  ROBSEG_REQUIRE(loss_kind >= ROBSEG_LOSS_CE && loss_kind <= ROBSEG_LOSS_ARGMAX,
+                 "unknown loss kind %d", loss_kind);
+  ROBSEG_REQUIRE(B > 0 && C > 0 && HW > 0, "bad shape B=%d C=%d HW=%lld", B, C, (long long)HW);
+  ROBSEG_REQUIRE((int64_t)B * ((HW + 31) / 32) < (1ll << 31), "too many tiles");
+  ROBSEG_REQUIRE(workspace && workspace_bytes >= robseg_loss_workspace_bytes(B, C, HW, dtype),
+                 "workspace too small (%zu bytes)", workspace_bytes);
+  ROBSEG_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "workspace must be 16B aligned");
+
+  LossParams p{};
+  p.logits = logits, p.labels = labels, p.class_w = class_w, p.grad_scale = grad_scale;
+  p.upstream = upstream_pix, p.dlogits = dlogits, p.loss_pix = loss_pix, p.pred = pred;
+  p.partials = static_cast<float4*>(workspace);
+  p.HW = HW, p.kind = loss_kind, p.ignore_index = ignore_index, p.B = B, p.C = C;
+  p.inv_hw = (float)(1.0 / (double)HW);
+
+  const int esize = dtype == ROBSEG_F32 ? 4 : 2;
+  auto al16 = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool tma_ok = (HW * esize) % 16 == 0 && C <= 256 && al16(logits) && al16(dlogits) &&
+                      al16(labels) && al16(pred) && al16(loss_pix) && al16(upstream_pix) &&
+                      (size_t)C * 32 * esize * (esize == 2 ? 2 : 1) * 2 <= kSmemBudget - 512;
+  int rc;
+  int tiles_per_img;
+  if (tma_ok) {
+    const int vec = pick_vec(C, esize);
+    tiles_per_img = (int)((HW + 32 * vec - 1) / (32 * vec));
+    if (dtype == ROBSEG_F32) {
+      rc = vec == 4 ? launch_tma<float, 4>(p, stream)
+                    : vec == 2 ? launch_tma<float, 2>(p, stream) : launch_tma<float, 1>(p, stream);
+    } else {
+      rc = vec == 8 ? launch_tma<__nv_bfloat16, 8>(p, stream)
+                    : vec == 4 ? launch_tma<__nv_bfloat16, 4>(p, stream)
+                               : launch_tma<__nv_bfloat16, 2>(p, stream);
+    }
+  } else {
+    tiles_per_img = (int)((HW + 31) / 32);
+    rc = dtype == ROBSEG_F32 ? launch_generic<float>(p, stream)
+                             : launch_generic<__nv_bfloat16>(p, stream);
+  }
+  if (rc != 0) return rc;
+  if (loss_img || track_img || correct_img || valid_img) {
+    loss_finalize_kernel<<<B, 256, 0, stream>>>(p.partials, tiles_per_img, grad_scale,
+                                                1.0 / (double)HW, loss_img, track_img,
+                                                correct_img, valid_img);
+    ROBSEG_LAUNCH_CHECK();
+  }
+  return 0;
+}

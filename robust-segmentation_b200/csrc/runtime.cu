@@ -1,0 +1,34 @@
+// Library-level plumbing: ABI version, thread-local error text, cached device properties.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace robseg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace robseg
+
+extern "C" int robseg_version(void) { return ROBSEG_ABI_VERSION; }
+
+extern "C" const char* robseg_last_error(void) { return robseg::g_err; }

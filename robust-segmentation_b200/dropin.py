@@ -1,0 +1,37 @@
+"""Swap the B200 modules into a checkout of the reference.
+
+    import robseg_b200.dropin as dropin        # (alias from __graft_entry__.load_package)
+    dropin.install("/path/to/Robust-Segmentation")
+    import tools.infer                         # now binds to the B200 attacker / evalSEA
+
+``install`` imports the reference's own ``semseg`` package (models, datasets, configs stay
+theirs), then rebinds exactly the names SURVEY.md section 8b lists: the ``semseg.attacker``
+module, ``semseg.val.{Pgd_Attack, Pgd_Attack_1, evaluate}``, ``semseg.metrics.Metrics``,
+``semseg.losses.{CrossEntropy, get_loss}`` and ``tools.worse_only.evalSEA``.
+"""
+import importlib
+import sys
+
+
+def install(reference_root=None):
+    from .semseg import attacker, losses, metrics, val
+    from .tools import worse_only
+
+    if reference_root is not None and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    ref = importlib.import_module("semseg")
+    sys.modules["semseg.attacker"] = attacker
+    ref.attacker = attacker
+    for modname, names, src in (
+        ("semseg.val", ("Pgd_Attack", "Pgd_Attack_1", "evaluate"), val),
+        ("semseg.metrics", ("Metrics",), metrics),
+        ("semseg.losses", ("CrossEntropy", "get_loss"), losses),
+        ("tools.worse_only", ("evalSEA",), worse_only),
+    ):
+        try:
+            m = importlib.import_module(modname)
+        except Exception:  # optional pieces of the reference may not import (missing deps)
+            continue
+        for n in names:
+            setattr(m, n, getattr(src, n))
+    return attacker

@@ -1,0 +1,392 @@
+"""Tensor-level wrappers over the C ABI, plus the ``torch.ops.robseg.*`` registrations.
+
+Every function here launches hand-written sm_100a kernels from librobseg_b200.so on the
+caller's current CUDA stream.  CPU tensors are rejected: there is no fallback path.
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+
+KIND_IDS = {
+    "ce": _lib.LOSS_CE, "ce-avg": _lib.LOSS_CE, "pgd": _lib.LOSS_CE,
+    "mask-ce-avg": _lib.LOSS_MASK_CE, "mask-ce-bal": _lib.LOSS_MASK_CE_BAL,
+    "js-avg": _lib.LOSS_JS, "argmax": _lib.LOSS_ARGMAX,
+}
+
+LossOut = namedtuple("LossOut", "loss_img track_img correct valid dlogits pred loss_pix")
+
+_workspaces = {}
+
+# Optional per-launch device timing (bench.py turns it on inside its timed region): every
+# wrapper brackets its C call with CUDA events on the launching stream and appends
+# (name, algorithmic_bytes, start_event, end_event) here.
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """Returns [(name, bytes, ms)]; call after a device synchronize."""
+    global _prof
+    rec, _prof = _prof or [], None
+    return [(n, b, s.elapsed_time(e)) for n, b, s, e in rec]
+
+
+class _timed:
+    def __init__(self, name, nbytes):
+        self.name, self.nbytes = name, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            self.e.record()
+            _prof.append((self.name, self.nbytes, self.s, self.e))
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("robseg-b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _workspace(dev, nbytes):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=None,
+                 want_grad=True, want_pred=False, want_loss_pix=False, ignore_index=-1,
+                 dlogits_out=None, want_stats=True):
+    """Fused softmax + loss + dlogits + argmax + per-image sums (robseg_loss_fwd_bwd).
+
+    logits [B,C,*spatial] fp32/bf16 (contiguous), labels [B,*spatial] int64.
+    grad_scale: None (1/HW per image), python float, or [B] tensor.
+    Returns LossOut; fields not requested are None.
+    """
+    _need_cuda(logits, labels, weights, upstream)
+    lib = _lib.load()
+    if logits.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"logits dtype {logits.dtype} not supported (fp32 / bf16)")
+    logits = logits.detach()
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    B, Cn = logits.shape[0], logits.shape[1]
+    HW = logits[0, 0].numel()
+    labels = labels.detach()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    labels = labels.contiguous()
+    if labels.numel() != B * HW:
+        raise ValueError(f"labels shape {tuple(labels.shape)} does not match logits {tuple(logits.shape)}")
+    dev = logits.device
+    kid = KIND_IDS[kind]
+    if weights is not None:
+        weights = weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if weights.numel() != Cn:
+            raise ValueError("class weights must have C entries")
+    if grad_scale is not None and not torch.is_tensor(grad_scale):
+        grad_scale = torch.full((B,), float(grad_scale), dtype=torch.float32, device=dev)
+    if grad_scale is not None:
+        grad_scale = grad_scale.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if grad_scale.numel() == 1:
+            grad_scale = grad_scale.reshape(1).expand(B).contiguous()
+    if upstream is not None:
+        upstream = upstream.detach().to(dtype=torch.float32).contiguous()
+    want_grad = want_grad and kid != _lib.LOSS_ARGMAX
+    if want_grad:
+        dlogits = dlogits_out if dlogits_out is not None else torch.empty_like(logits)
+        if dlogits.shape != logits.shape or dlogits.dtype != logits.dtype or not dlogits.is_contiguous():
+            raise ValueError("dlogits_out must match logits")
+    else:
+        dlogits = None
+    spatial = logits.shape[2:]
+    pred = torch.empty((B, *spatial), dtype=torch.int64, device=dev) if want_pred else None
+    loss_pix = torch.empty((B, *spatial), dtype=torch.float32, device=dev) if want_loss_pix else None
+    if want_stats:
+        fstat = torch.empty((2, B), dtype=torch.float32, device=dev)
+        istat = torch.empty((2, B), dtype=torch.int32, device=dev)
+    else:
+        fstat = istat = None
+    dt = _lib.F32 if logits.dtype == torch.float32 else _lib.BF16
+    nws = lib.robseg_loss_workspace_bytes(B, Cn, HW, dt)
+    ws = _workspace(dev, nws)
+    # algorithmic bytes: logits read (+ gradient write) + int64 labels
+    # (+ int64 argmax)
+    nbytes = B * Cn * HW * logits.element_size() * (2 if want_grad else 1) + 8 * B * HW * (2 if want_pred else 1)
+    with torch.cuda.device(dev), _timed("loss_grad" if want_grad else "loss_only", nbytes):
+        rc = lib.robseg_loss_fwd_bwd(
+            logits.data_ptr(), dt, labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn,
+            HW, _ptr(grad_scale), _ptr(upstream), _ptr(dlogits), _ptr(loss_pix), _ptr(pred),
+            _ptr(fstat[0]) if want_stats else 0, _ptr(fstat[1]) if want_stats else 0,
+            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0,
+            ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "robseg_loss_fwd_bwd")
+    _lib.count(2 if want_stats else 1)
+    if want_stats:
+        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlogits, pred, loss_pix)
+    return LossOut(None, None, None, None, dlogits, pred, loss_pix)
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+    return t
+
+
+def apgd_step(x, x_adv, x_old, grad, step, eps, a, out):
+    """out <- one L-inf APGD update (robseg_apgd_step); bit-exact with attacker.py:388-410."""
+    _need_cuda(x, x_adv, x_old, grad, step, out)
+    lib = _lib.load()
+    for n, t in (("x", x), ("x_adv", x_adv), ("x_old", x_old), ("grad", grad), ("step", step), ("out", out)):
+        _f32c(t, n)
+    B = x.shape[0]
+    with torch.cuda.device(x.device), _timed("apgd_step", 20 * x.numel()):
+        rc = lib.robseg_apgd_step(x.data_ptr(), x_adv.data_ptr(), x_old.data_ptr(), grad.data_ptr(),
+                                  step.data_ptr(), float(eps), float(a), float(1.0 - a), B,
+                                  x[0].numel(), out.data_ptr(), _stream())
+    _lib.check(rc, "robseg_apgd_step")
+    _lib.count(1)
+    return out
+
+
+def project_linf(z, x, eps, noise=None, out=None):
+    """clip01(x + clip(z-x, +-eps)), or with noise: clip01(x + eps*noise) (robseg_project_linf)."""
+    _need_cuda(z, x, noise, out)
+    lib = _lib.load()
+    _f32c(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    _f32c(out, "out")
+    if z is not None:
+        _f32c(z, "z")
+    if noise is not None:
+        _f32c(noise, "noise")
+    with torch.cuda.device(x.device):
+        rc = lib.robseg_project_linf(_ptr(z), x.data_ptr(), _ptr(noise), float(eps), x.numel(),
+                                     out.data_ptr(), _stream())
+    _lib.check(rc, "robseg_project_linf")
+    _lib.count(1)
+    return out
+
+
+def pgd_step(X, delta, grad, alpha, eps, mask_outside=False, x_next=None, clamp_next=True):
+    """In-place PIR-AT delta update (robseg_pgd_step), optionally emitting the next input."""
+    _need_cuda(X, delta, grad, x_next)
+    lib = _lib.load()
+    for n, t in (("X", X), ("delta", delta), ("grad", grad)):
+        _f32c(t, n)
+    if x_next is not None:
+        _f32c(x_next, "x_next")
+    with torch.cuda.device(X.device):
+        rc = lib.robseg_pgd_step(X.data_ptr(), delta.data_ptr(), grad.data_ptr(), float(alpha),
+                                 float(eps), int(mask_outside), int(clamp_next), X.numel(),
+                                 _ptr(x_next), _stream())
+    _lib.check(rc, "robseg_pgd_step")
+    _lib.count(1)
+    return delta
+
+
+def apgd_bookkeep(correct, valid, loss_indiv, acc, loss_best, loss_best_last, reduced_last, step,
+                  loss_steps, it, check_k, HW, early_stop, flags, done):
+    """Device-side step-size / best-point bookkeeping (robseg_apgd_bookkeep)."""
+    lib = _lib.load()
+    n_iter, B = loss_steps.shape
+    with torch.cuda.device(acc.device), _timed("bookkeep", 0):
+        rc = lib.robseg_apgd_bookkeep(
+            correct.data_ptr(), valid.data_ptr(), loss_indiv.data_ptr(), acc.data_ptr(),
+            loss_best.data_ptr(), loss_best_last.data_ptr(), reduced_last.data_ptr(),
+            step.data_ptr(), loss_steps.data_ptr(), n_iter, int(it), int(check_k), B, int(HW),
+            int(bool(early_stop)), flags.data_ptr(), done.data_ptr(), 0, _stream())
+    _lib.check(rc, "robseg_apgd_bookkeep")
+    _lib.count(1)
+    return flags
+
+
+def row_select(jobs, B, device):
+    """jobs: list of (dst, src, flags[B] int32, unless[B] int32 | None); rows dst[b] <- src[b]."""
+    lib = _lib.load()
+    arr = (_lib.RowJob * len(jobs))()
+    for k, (dst, src, flags, unless) in enumerate(jobs):
+        if dst.shape != src.shape or dst.dtype != src.dtype:
+            raise ValueError("row_select: dst/src mismatch")
+        if not (dst.is_contiguous() and src.is_contiguous()):
+            raise ValueError("row_select: tensors must be contiguous")
+        arr[k] = _lib.RowJob(dst.data_ptr(), src.data_ptr(), flags.data_ptr(), _ptr(unless),
+                             dst[0].numel() * dst.element_size())
+    with torch.cuda.device(device), _timed("row_select", 0):
+        rc = lib.robseg_row_select(arr, len(jobs), B, _stream())
+    _lib.check(rc, "robseg_row_select")
+    _lib.count(1)
+
+
+def pixel_hist(pred, labels, n_cls, ignore_index=-1, want_hist=False, hist_total=None,
+               want_counts=True):
+    """Integer confusion / intersection / union counters (robseg_pixel_hist).
+
+    pred [n_img,*spatial] int64, labels [n_lab,*spatial] int64 with n_img % n_lab == 0
+    (image i is scored against labels[i % n_lab]).  Returns dict of int64 tensors:
+    hist [n_img,C,C] (if want_hist), inter/tgt/prd [n_img,C] (if want_counts); hist_total
+    [C,C] int64 is accumulated in place when given."""
+    _need_cuda(pred, labels, hist_total)
+    lib = _lib.load()
+    pred = pred.detach()
+    labels = labels.detach()
+    if pred.dtype != torch.int64:
+        pred = pred.long()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    pred, labels = pred.contiguous(), labels.contiguous()
+    n_img, n_lab = pred.shape[0], labels.shape[0]
+    HW = pred[0].numel()
+    if labels[0].numel() != HW or n_img % n_lab != 0:
+        raise ValueError("pred / labels shape mismatch")
+    dev = pred.device
+    out = {}
+    if want_hist:
+        out["hist"] = torch.zeros((n_img, n_cls, n_cls), dtype=torch.int64, device=dev)
+    if want_counts:
+        cnt = torch.zeros((3, n_img, n_cls), dtype=torch.int64, device=dev)
+        out["inter"], out["tgt"], out["prd"] = cnt[0], cnt[1], cnt[2]
+    if hist_total is not None and (hist_total.dtype != torch.int64 or not hist_total.is_contiguous()):
+        raise TypeError("hist_total must be contiguous int64")
+    with torch.cuda.device(dev), _timed("pixel_hist", 16 * n_img * HW):
+        rc = lib.robseg_pixel_hist(pred.data_ptr(), labels.data_ptr(), n_img, n_lab, HW, int(n_cls),
+                                   int(ignore_index), _ptr(out.get("hist")), _ptr(hist_total),
+                                   _ptr(out.get("inter")), _ptr(out.get("tgt")), _ptr(out.get("prd")),
+                                   _stream())
+    _lib.check(rc, "robseg_pixel_hist")
+    _lib.count(1)
+    return out
+
+
+def sea_worst_acc(inter, tgt):
+    """inter/tgt [A,N,C] int64 -> (acc[A,N] f32, worst[N] f32) (robseg_sea_worst_acc)."""
+    _need_cuda(inter, tgt)
+    lib = _lib.load()
+    inter, tgt = inter.contiguous(), tgt.contiguous()
+    A, N, Cn = inter.shape
+    acc = torch.empty((A, N), dtype=torch.float32, device=inter.device)
+    worst = torch.empty((N,), dtype=torch.float32, device=inter.device)
+    with torch.cuda.device(inter.device):
+        rc = lib.robseg_sea_worst_acc(inter.data_ptr(), tgt.data_ptr(), A, N, Cn, acc.data_ptr(),
+                                      worst.data_ptr(), _stream())
+    _lib.check(rc, "robseg_sea_worst_acc")
+    _lib.count(1)
+    return acc, worst
+
+
+# ----------------------------------------------------------------------------------------------
+# torch.ops.robseg.* : the same kernels as dispatcher-visible custom ops.  ``pixel_loss`` carries
+# an autograd formula so the criterion_dict-compatible callables stay differentiable.
+# ----------------------------------------------------------------------------------------------
+_registered = False
+
+
+def register_custom_ops():
+    global _registered
+    if _registered:
+        return
+    _registered = True
+    lib = torch.library
+
+    @lib.custom_op("robseg::pixel_loss", mutates_args=())
+    def pixel_loss(logits: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor, kind: str,
+                   ignore_index: int) -> torch.Tensor:
+        w = weights if weights.numel() else None
+        return loss_fwd_bwd(logits, labels, kind, w, want_grad=False, want_loss_pix=True,
+                            ignore_index=ignore_index, want_stats=False).loss_pix
+
+    @pixel_loss.register_fake
+    def _(logits, labels, weights, kind, ignore_index):
+        return logits.new_empty((logits.shape[0], *logits.shape[2:]), dtype=torch.float32)
+
+    @lib.custom_op("robseg::pixel_loss_bwd", mutates_args=())
+    def pixel_loss_bwd(logits: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor, kind: str,
+                       ignore_index: int, gout: torch.Tensor) -> torch.Tensor:
+        w = weights if weights.numel() else None
+        return loss_fwd_bwd(logits, labels, kind, w, grad_scale=1.0, upstream=gout, want_grad=True,
+                            ignore_index=ignore_index, want_stats=False).dlogits
+
+    @pixel_loss_bwd.register_fake
+    def _(logits, labels, weights, kind, ignore_index, gout):
+        return torch.empty_like(logits)
+
+    def _setup(ctx, inputs, output):
+        logits, labels, weights, kind, ignore_index = inputs
+        ctx.save_for_backward(logits, labels, weights)
+        ctx.kind, ctx.ignore_index = kind, ignore_index
+
+    def _backward(ctx, gout):
+        logits, labels, weights = ctx.saved_tensors
+        g = torch.ops.robseg.pixel_loss_bwd(logits, labels, weights, ctx.kind, ctx.ignore_index,
+                                            gout.contiguous())
+        return g, None, None, None, None
+
+    pixel_loss.register_autograd(_backward, setup_context=_setup)
+
+    @lib.custom_op("robseg::loss_fwd_bwd", mutates_args=())
+    def loss_fwd_bwd_op(logits: torch.Tensor, labels: torch.Tensor, weights: torch.Tensor, kind: str,
+                        ignore_index: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor,
+                                                     torch.Tensor, torch.Tensor, torch.Tensor]:
+        w = weights if weights.numel() else None
+        o = loss_fwd_bwd(logits, labels, kind, w, want_grad=True, want_pred=True,
+                         ignore_index=ignore_index)
+        return o.dlogits, o.loss_img.clone(), o.track_img.clone(), o.correct.clone(), o.valid.clone(), o.pred
+
+    @loss_fwd_bwd_op.register_fake
+    def _(logits, labels, weights, kind, ignore_index):
+        B = logits.shape[0]
+        f = logits.new_empty((B,), dtype=torch.float32)
+        i = logits.new_empty((B,), dtype=torch.int32)
+        return (torch.empty_like(logits), f, f.clone(), i, i.clone(),
+                logits.new_empty((B, *logits.shape[2:]), dtype=torch.int64))
+
+    @lib.custom_op("robseg::apgd_step", mutates_args=())
+    def apgd_step_op(x: torch.Tensor, x_adv: torch.Tensor, x_old: torch.Tensor, grad: torch.Tensor,
+                     step: torch.Tensor, eps: float, a: float) -> torch.Tensor:
+        return apgd_step(x, x_adv, x_old, grad, step, eps, a, torch.empty_like(x))
+
+    @apgd_step_op.register_fake
+    def _(x, x_adv, x_old, grad, step, eps, a):
+        return torch.empty_like(x)
+
+    @lib.custom_op("robseg::pixel_hist", mutates_args=())
+    def pixel_hist_op(pred: torch.Tensor, labels: torch.Tensor, n_cls: int,
+                      ignore_index: int) -> torch.Tensor:
+        return pixel_hist(pred, labels, n_cls, ignore_index, want_hist=True, want_counts=False)["hist"]
+
+    @pixel_hist_op.register_fake
+    def _(pred, labels, n_cls, ignore_index):
+        return pred.new_empty((pred.shape[0], n_cls, n_cls), dtype=torch.int64)
+
+
+def pixel_loss(logits, labels, kind, weights=None, ignore_index=-1):
+    """Differentiable per-pixel criterion [B,*spatial] (criterion_dict semantics)."""
+    register_custom_ops()
+    w = weights if weights is not None else logits.new_empty((0,), dtype=torch.float32)
+    w = w.to(device=logits.device, dtype=torch.float32)
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    return torch.ops.robseg.pixel_loss(logits.contiguous(), labels.contiguous(), w, kind, ignore_index)

@@ -1,0 +1,191 @@
+"""B200 drop-in for the reference's ``tools/worse_only.py`` (``evalSEA``, :96-422).
+
+Worst-case SEA aggregation over the per-attack argmax maps:
+
+* the per-attack, per-image, per-class intersection / target / prediction counts
+  (``update_fn_indiv`` :49-66, the class loops of ``worse_case_eval`` :383-394) come from ONE
+  ``robseg_pixel_hist`` launch over the stacked ``[A*N, H*W]`` predictions -- exact int64
+  counters instead of ``A*N*2*C`` float32 reductions with a bs=1 DataLoader;
+* the image-wise worst aACC (``:396-408``) is ``robseg_sea_worst_acc`` (fp32 division of the
+  exact sums, min over attacks); only the final means over N images are taken with the
+  same ``torch`` CPU ops as the reference so the reported float is bit-identical;
+* the greedy randomised worst-case mIoU (``:267-334``) is inherently sequential and stays on
+  the host.  It replays the reference's arithmetic exactly: float32 running sums, Python
+  double ratios with the ``+1e-8`` in the candidate score, and ``statistics.mean``'s
+  correctly rounded exact mean (computed here with integer arithmetic, ~10x faster).
+
+Known deviations: Q5 -- a ragged last batch is indexed correctly
+(the reference's ``i*BS`` offset is wrong there; identical when ``N % bs == 0``); Q8 -- classes
+whose running union is 0 stay aligned (the reference shortens its lists and mis-aligns
+classes; identical when every class occurs); Q9 -- the never-hit stats cache is not read.
+"""
+import os
+import random
+
+import numpy as np
+import torch
+import torch.utils.data as data
+
+from .. import ops
+
+SEED = 225
+random.seed(SEED)
+np.random.seed(SEED)
+
+_TWO53 = float(2 ** 53)
+
+
+def exact_mean(values):
+    """Correctly rounded mean of a float64 vector == ``statistics.mean(list)``.
+
+    Every double is m * 2**e with an integer 53-bit m; the sum is accumulated in Python's
+    arbitrary-precision integers and the final int/int true division is correctly rounded."""
+    values = np.asarray(values, dtype=np.float64)
+    n = values.size
+    if n == 0:
+        raise ValueError("mean requires at least one data point")
+    mant, exp = np.frexp(values)
+    mi = (mant * _TWO53).astype(np.int64)
+    emin = int(exp.min())
+    total = 0
+    for m, e in zip(mi.tolist(), (exp - emin).tolist()):
+        total += m << e
+    k = emin - 53
+    if k >= 0:
+        return (total << k) / n
+    return total / (n << (-k))
+
+
+def _f32(v):
+    return np.asarray(v, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def _compute_miou(inters, union):
+    """tools/worse_only.py:69-76 on float64 vectors holding float32-rounded values."""
+    keep = union != 0
+    return exact_mean(inters[keep] / union[keep])
+
+
+def greedy_worst_miou(cons_ints, cons_unions, n_rounds=1000, rng=random):
+    """tools/worse_only.py:267-334.  cons_*: [A,N,C] exact counts.  Returns (miou, selection)."""
+    ci = np.asarray(cons_ints, dtype=np.float64)
+    cu = np.asarray(cons_unions, dtype=np.float64)
+    A, N, _ = ci.shape
+    # running sums start from attack 0, accumulated image by image in float32 (:236-246)
+    run_i = np.add.accumulate(ci[0].astype(np.float32), axis=0)[-1].astype(np.float64)
+    run_u = np.add.accumulate(cu[0].astype(np.float32), axis=0)[-1].astype(np.float64)
+    final = _compute_miou(run_i, run_u)
+    sel = [0] * N
+    prev_best = 10
+    for _ in range(n_rounds):
+        order = list(range(0, N))
+        rng.shuffle(order)
+        for idx in order:
+            for a in range(A):
+                ri, ru = _f32(run_i), _f32(run_u)       # torch.tensor(list) -> float32 (:311-312)
+                new_i = ri + (ci[a, idx] - ci[sel[idx], idx])
+                new_u = ru + (cu[a, idx] - cu[sel[idx], idx])
+                keep = ru != 0
+                est = exact_mean(new_i[keep] / (new_u[keep] + 1e-8))
+                if est < final:
+                    sel[idx] = a
+                    run_i, run_u = new_i, new_u
+            final = _compute_miou(_f32(run_i), _f32(run_u))
+        if prev_best - final <= 1e-6:
+            break
+        prev_best = final
+    return final, sel
+
+
+class evalSEA:
+    """Worst-case SEA evaluation; same constructor and methods as the reference (:143-166)."""
+
+    def __init__(self, val_data, l_outs, eps, n_cls, addendum, saveDir, saveDict, modelName,
+                 device=None):
+        self.val_data = val_data
+        self.l_output = l_outs
+        self.eps = eps
+        self.addendum = addendum
+        self.saveDir = saveDir
+        self.saveDict = saveDict
+        self.modelName = modelName
+        self.n_cls = n_cls
+        self.los_pairs = ["mask-ce-bal", "mask-ce-avg", "js-avg"]
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self._counts = None
+
+    def get_loader(self, bs=1):
+        return data.DataLoader(self.val_data, batch_size=bs, shuffle=False, num_workers=0)
+
+    def _load_outputs(self):
+        if not self.l_output:
+            self.l_output = [
+                torch.load(self.saveDir + f"/argmax-logs/{self.modelName}_{loss_}_{self.eps}.pt")
+                for loss_ in self.los_pairs]
+        return torch.stack(self.l_output, dim=0)
+
+    def _targets(self, n_max):
+        """[N,H,W] int64 targets of the first n_max dataset items (item = (img, target, name))."""
+        if isinstance(self.val_data, torch.Tensor):
+            return self.val_data[:n_max]
+        out = []
+        for i, vals in enumerate(self.get_loader(bs=16)):
+            out.append(vals[1])
+            if sum(t.shape[0] for t in out) >= n_max:
+                break
+        return torch.cat(out)[:n_max]
+
+    def per_image_counts(self, n_images=None):
+        """Exact int64 (inter, tgt, prd) of shape [A,N,C], computed once on the device."""
+        if self._counts is not None and (n_images is None or self._counts[0].shape[1] == n_images):
+            return self._counts
+        preds = self._load_outputs()
+        A, N = preds.shape[:2]
+        if n_images is not None:
+            N = min(N, n_images)
+        target = self._targets(N)
+        N = min(N, target.shape[0])
+        inter = torch.zeros((A, N, self.n_cls), dtype=torch.int64, device=self.device)
+        tgt, prd = torch.zeros_like(inter), torch.zeros_like(inter)
+        chunk = max(1, (1 << 28) // max(1, preds[0, 0].numel() * 8 * A))  # ~256 MB of preds per launch
+        for s in range(0, N, chunk):
+            e = min(N, s + chunk)
+            p = preds[:, s:e].to(self.device, non_blocking=True).reshape(A * (e - s), -1)
+            t = target[s:e].to(self.device, non_blocking=True).reshape(e - s, -1)
+            c = ops.pixel_hist(p, t, self.n_cls, -1)
+            inter[:, s:e] = c["inter"].view(A, e - s, -1)
+            tgt[:, s:e] = c["tgt"].view(A, e - s, -1)
+            prd[:, s:e] = c["prd"].view(A, e - s, -1)
+        self._counts = (inter, tgt, prd)
+        return self._counts
+
+    def worse_case_eval(self, bs=16, n_batches=-1):
+        """Worst aACC across the three attacks, image-wise (:351-422)."""
+        n_img = None if n_batches is None or n_batches < 0 else bs * n_batches
+        inter, tgt, _ = self.per_image_counts(n_img)
+        acc_an, _ = ops.sea_worst_acc(inter, tgt)
+        final_acc_1 = acc_an.cpu()
+        worse_1 = final_acc_1.min(0)[0].mean()
+        at_w_sum1 = final_acc_1.mean(-1)
+        print("SEA evaluated Acc", worse_1)
+        self.saveDict["worst_Acc"] = worse_1.item()
+        self.saveDict["worst_Acc_indiv"] = at_w_sum1
+
+    def worst_case_miou(self):
+        """Image-wise worst-case mIoU by greedy randomised reassignment (:181-349)."""
+        inter, tgt, prd = self.per_image_counts()
+        union = tgt + prd - inter
+        cons_ints = inter.cpu().to(torch.float32)
+        cons_unions = union.cpu().to(torch.float32)
+        stats_dir = os.path.join(self.saveDir, "test_results")
+        if os.path.isdir(stats_dir):  # same on-disk record as the reference (:255-265)
+            torch.save({"run_int_imwise": cons_ints, "run_union_imwise": cons_unions,
+                        "run_intersect_abs": list(cons_ints[0].sum(0)),
+                        "run_union_abs": list(cons_unions[0].sum(0))},
+                       os.path.join(stats_dir, f"stats_{self.addendum}_{self.eps}.pt"))
+        final_miou, sel = greedy_worst_miou(inter.cpu().numpy(), union.cpu().numpy())
+        self.saveDict["seed"] = SEED
+        self.saveDict["final_miou"] = final_miou
+        self.selected_attack = sel
+        print("SEA Evaluation complete, saved-dict:")
+        print(self.saveDict)

@@ -1,0 +1,464 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI / public Python surface) against
+the CPU oracle and the committed golden vectors of the reference.  Run on the B200 box:
+``python -m pytest tests -m gpu``.
+
+Tolerances (BASELINE.json north_star): integer / index outputs bit-exact; fp32 losses and
+logit-gradients <= 1e-5 relative; bf16 <= 1e-2; the APGD / PGD updates bit-exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import robseg_oracle as O
+
+pytestmark = pytest.mark.gpu
+KINDS = ["mask-ce-avg", "mask-ce-bal", "js-avg", "ce-avg"]
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    from importlib import import_module
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    names = dict(ops=".ops", lib="._lib", attacker=".semseg.attacker", val=".semseg.val",
+                 metrics=".semseg.metrics", losses=".semseg.losses", worse=".tools.worse_only",
+                 infer=".tools.infer", consumers=".consumers")
+    return type("M", (), {k: import_module("robseg_b200" + v) for k, v in names.items()})
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def make_problem(B, C, H, W, seed, sigma=3.0, frac_ignore=0.1, bf16=False):
+    g = torch.Generator().manual_seed(seed)
+    z = sigma * torch.randn(B, C, H, W, generator=g)
+    if bf16:
+        z = z.bfloat16().float()
+    y = torch.randint(0, C, (B, H, W), generator=g)
+    y = torch.where(torch.rand(B, H, W, generator=g) < 0.5, z.argmax(1), y)
+    y = torch.where(torch.rand(B, H, W, generator=g) < frac_ignore, torch.full_like(y, -1), y)
+    w = 0.5 + torch.rand(C, generator=g)
+    return z, y, w
+
+
+# shapes: TMA path VEC=4 (C<=48), VEC=2, VEC=1 (C=150/151), partial last tile, and shapes that
+# force the generic path (HW*4 % 16 != 0)
+SHAPES = [(2, 21, 32, 32), (2, 7, 5, 6), (1, 64, 16, 24), (1, 150, 24, 24), (2, 151, 16, 20),
+          (1, 21, 33, 37), (1, 151, 13, 11), (3, 2, 8, 8), (1, 256, 8, 8), (1, 300, 6, 6)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("kind", KINDS)
+def test_loss_kernel_vs_oracle_fp32(mods, shape, kind):
+    B, C, H, W = shape
+    z, y, w = make_problem(B, C, H, W, seed=hash(shape) % 1000)
+    out = mods.ops.loss_fwd_bwd(z.to(dev()), y.to(dev()), kind, w.to(dev()), want_pred=True,
+                                want_loss_pix=True)
+    ref = O.loss_fwd_bwd(z.numpy().reshape(B, C, -1), y.numpy().reshape(B, -1), kind, w.numpy())
+    assert np.array_equal(out.pred.cpu().numpy().reshape(B, -1), ref["pred"])
+    assert np.array_equal(out.correct.cpu().numpy(), ref["correct"])
+    assert np.array_equal(out.valid.cpu().numpy(), ref["valid"])
+    assert rel(out.dlogits.cpu().numpy().reshape(B, C, -1), ref["dlogits"]) <= 1e-5
+    assert rel(out.loss_pix.cpu().numpy().reshape(B, -1), ref["loss_pix"]) <= 1e-5
+    np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(out.track_img.cpu().numpy(), ref["track_img"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("tag", ["c7", "c21", "c151"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_loss_kernel_vs_reference_golden(mods, golden, tag, kind):
+    """Directly against what the reference's own functions + autograd returned."""
+    g = golden("loss_" + tag)
+    k = kind.replace("-", "_")
+    z, y, w = (torch.from_numpy(g[n]).to(dev()) for n in ("logits", "labels", "weights"))
+    out = mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_loss_pix=True)
+    assert rel(out.loss_pix.cpu().numpy(), g[k + "__loss_pix"]) <= 1e-5
+    assert rel(out.dlogits.cpu().numpy(), g[k + "__dlogits"]) <= 1e-5
+    np.testing.assert_allclose(out.loss_img.cpu().numpy(), g[k + "__loss_img"], rtol=1e-5)
+    assert np.array_equal(out.pred.cpu().numpy(), g["pred"])  # ties -> lowest index
+    P = g["labels"][0].size
+    assert np.array_equal((out.correct.float() / P).cpu().numpy(), g["acc_step0"])
+    loop = ((out.correct + (P - out.valid)).float() / P).cpu().numpy()
+    assert np.array_equal(loop, g["acc_loop"])
+    # criterion_dict-compatible differentiable op, arbitrary upstream gradient
+    crit = mods.attacker.criterion_dict[kind]
+    zz = z.clone().requires_grad_()
+    lp = crit(zz, y, w)
+    assert rel(lp.detach().cpu().numpy(), g[k + "__loss_pix"]) <= 1e-5
+    up = torch.from_numpy(g[k + "__upstream"]).to(dev())
+    (gz,) = torch.autograd.grad((lp * up).sum(), [zz])
+    assert rel(gz.cpu().numpy(), g[k + "__dlogits_up"]) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 32, 32), (1, 150, 32, 32), (1, 151, 16, 24), (1, 21, 9, 7)])
+@pytest.mark.parametrize("kind", KINDS)
+def test_loss_kernel_bf16(mods, shape, kind):
+    B, C, H, W = shape
+    z, y, w = make_problem(B, C, H, W, seed=7, bf16=True)
+    out = mods.ops.loss_fwd_bwd(z.to(dev()).bfloat16(), y.to(dev()), kind, w.to(dev()), want_pred=True)
+    ref = O.loss_fwd_bwd(z.numpy().reshape(B, C, -1), y.numpy().reshape(B, -1), kind, w.numpy())
+    assert out.dlogits.dtype == torch.bfloat16
+    assert np.array_equal(out.pred.cpu().numpy().reshape(B, -1), ref["pred"])  # bf16 ties included
+    assert np.array_equal(out.correct.cpu().numpy(), ref["correct"])
+    assert rel(out.dlogits.float().cpu().numpy().reshape(B, C, -1), ref["dlogits"]) <= 1e-2
+    np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
+
+
+def test_loss_kernel_edge_cases(mods):
+    o = mods.ops
+    # all pixels ignored; all pixels wrong (mask empty); all correct; saturated logits (JS finite)
+    B, C, H, W = 2, 21, 16, 16
+    z, y, w = make_problem(B, C, H, W, 3)
+    out = o.loss_fwd_bwd(z.to(dev()), torch.full_like(y, -1).to(dev()), "mask-ce-avg", None)
+    assert float(out.dlogits.abs().max()) == 0 and float(out.loss_img.abs().max()) == 0
+    assert out.valid.tolist() == [0, 0]
+    wrong = (z.argmax(1) + 1) % C
+    out = o.loss_fwd_bwd(z.to(dev()), wrong.to(dev()), "mask-ce-avg", None)
+    assert float(out.dlogits.abs().max()) == 0 and out.correct.tolist() == [0, 0]
+    assert float(out.track_img.min()) > 0
+    out = o.loss_fwd_bwd(z.to(dev()), z.argmax(1).to(dev()), "mask-ce-avg", None)
+    assert out.correct.tolist() == [H * W, H * W]
+    zs = z.clone()
+    zs[:, 0] += 300.0
+    out = o.loss_fwd_bwd(zs.to(dev()), y.clamp(min=0).to(dev()), "js-avg", None)
+    assert torch.isfinite(out.dlogits).all() and torch.isfinite(out.loss_img).all()
+    with pytest.raises(RuntimeError):
+        o.loss_fwd_bwd(z, y, "ce")  # CPU tensors: no fallback
+
+
+def test_loss_kernel_properties_full_size(mods):
+    """BASELINE config-2-sized tile stream (C=150, 512x512): size-independent properties."""
+    o = mods.ops
+    B, C, H, W = 2, 150, 512, 512
+    g = torch.Generator(device="cuda").manual_seed(0)
+    z = 3 * torch.randn(B, C, H, W, device=dev(), generator=g)
+    y = torch.randint(0, C, (B, H, W), device=dev(), generator=g)
+    y = torch.where(torch.rand(B, H, W, device=dev(), generator=g) < 0.5, z.argmax(1), y)
+    w = 0.5 + torch.rand(C, device=dev(), generator=g)
+    for kind in KINDS:
+        a = o.loss_fwd_bwd(z, y, kind, w, want_pred=True)
+        b = o.loss_fwd_bwd(z, y, kind, w, want_pred=True)
+        assert torch.equal(a.dlogits, b.dlogits) and torch.equal(a.loss_img, b.loss_img)  # deterministic
+        assert torch.equal(a.pred, z.argmax(1))
+        assert torch.equal(a.correct.long(), (z.argmax(1) == y).flatten(1).sum(1))
+        assert float(a.dlogits.sum(1).abs().max()) <= 2e-9  # softmax gradient sums to zero
+        lo = o.loss_fwd_bwd(z, y, kind, w, want_grad=False)
+        assert torch.equal(lo.loss_img, a.loss_img) and torch.equal(lo.track_img, a.track_img)
+        if kind.startswith("mask"):
+            miss = (a.pred != y)
+            assert float(a.dlogits.permute(0, 2, 3, 1)[miss].abs().max()) == 0
+        ce = torch.nn.functional.cross_entropy(z, y, reduction="none").flatten(1).mean(1)
+        assert torch.allclose(a.track_img, ce, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 16, 16), (2, 3, 7, 5), (16, 3, 64, 64)])
+def test_apgd_step_bit_exact(mods, shape):
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(shape, generator=g)
+    eps = 8 / 255
+    xa = (x + eps * (2 * torch.rand(shape, generator=g) - 1)).clamp(0, 1)
+    xo = (x + eps * (2 * torch.rand(shape, generator=g) - 1)).clamp(0, 1)
+    gr = torch.randn(shape, generator=g)
+    gr[0, 0, 0, :3] = 0.0
+    step = torch.tensor([2 * eps / (2 ** (i % 3)) for i in range(shape[0])], dtype=torch.float32)
+    for a in (1.0, 0.75):
+        out = torch.empty_like(x).to(dev())
+        mods.ops.apgd_step(x.to(dev()), xa.to(dev()), xo.to(dev()), gr.to(dev()), step.to(dev()), eps, a, out)
+        ref = O.apgd_step(x.numpy(), xa.numpy(), xo.numpy(), gr.numpy(), step.numpy(), eps, a)
+        assert np.array_equal(out.cpu().numpy(), ref)
+        # and against the ATen op chain of the reference (semseg/attacker.py:395-410)
+        X, XA, XO, G, S = (t.to(dev()) for t in (x, xa, xo, gr, step.view(-1, 1, 1, 1)))
+        g2 = XA - XO
+        z = XA + S * torch.sign(G)
+        z = torch.clamp(torch.min(torch.max(z, X - eps), X + eps), 0.0, 1.0)
+        z = torch.clamp(torch.min(torch.max(XA + (z - XA) * a + g2 * (1 - a), X - eps), X + eps), 0.0, 1.0)
+        assert torch.equal(out, z)
+
+
+def test_project_and_pgd_step_bit_exact(mods):
+    g = torch.Generator().manual_seed(2)
+    shape = (2, 3, 9, 11)
+    x = torch.rand(shape, generator=g)
+    z = (x + 0.1 * torch.randn(shape, generator=g))
+    eps = 6 / 255
+    out = mods.ops.project_linf(z.to(dev()), x.to(dev()), eps)
+    assert np.array_equal(out.cpu().numpy(), O.project_linf(z.numpy(), x.numpy(), eps))
+    t = 2 * torch.rand(shape, generator=g) - 1
+    out = mods.ops.project_linf(None, x.to(dev()), eps, noise=t.to(dev()))
+    assert np.array_equal(out.cpu().numpy(), O.random_start(x.numpy(), eps, t.numpy()))
+    delta = (eps * (2 * torch.rand(shape, generator=g) - 1))
+    gr = torch.randn(shape, generator=g)
+    d = delta.clone().to(dev())
+    xn = torch.empty_like(d)
+    mods.ops.pgd_step(x.to(dev()), d, gr.to(dev()), 1e-2, eps, mask_outside=False, x_next=xn, clamp_next=False)
+    ref = O.pgd_step(x.numpy(), delta.numpy(), gr.numpy(), 1e-2, eps)
+    assert np.array_equal(d.cpu().numpy(), ref)
+    assert np.array_equal(xn.cpu().numpy(), x.numpy() + ref)
+
+
+def test_bookkeeping_teacher_forced(mods):
+    """Random per-iteration (loss, accuracy) streams: device state == oracle state, every
+    iteration, including the oscillation checks, restarts and the early-stop freeze."""
+    rng = np.random.default_rng(0)
+    B, HW, n_iter, D = 5, 64, 40, 12
+    checks = dict(O.apgd_schedule(n_iter))
+    assert checks == mods.attacker.apgd_schedule(n_iter)
+    x0 = rng.random((B, D), dtype=np.float32)
+    g0 = rng.standard_normal((B, D)).astype(np.float32)
+    l0 = rng.random(B).astype(np.float32)
+    acc0 = (rng.integers(0, HW, B) / np.float32(HW)).astype(np.float32)
+    st = O.ApgdState(x0, g0, l0, acc0, np.zeros((B, 1), np.int64), n_iter, 8 / 255)
+    t = lambda a, dt=torch.float32: torch.tensor(np.asarray(a), dtype=dt, device=dev())
+    acc, lb, lbl, red = t(acc0), t(l0), t(l0), torch.ones(B, device=dev())
+    step = t(st.step)
+    ls = torch.zeros(n_iter, B, device=dev())
+    xb, xba, gb = t(x0), t(x0), t(g0)
+    flags = torch.zeros(3, B, dtype=torch.int32, device=dev())
+    done = torch.zeros(1, dtype=torch.int32, device=dev())
+    for i in range(n_iter):
+        x_i = rng.random((B, D), dtype=np.float32)
+        g_i = rng.standard_normal((B, D)).astype(np.float32)
+        loss = (rng.random(B) * (1 + 0.05 * i * (rng.random(B) > 0.5))).astype(np.float32)
+        valid = rng.integers(HW - 4, HW + 1, B).astype(np.int32)
+        correct = np.minimum(rng.integers(0, HW // 2, B), valid).astype(np.int32)
+        avg_acc = ((correct + (HW - valid)).astype(np.float32) / np.float32(HW)).astype(np.float32)
+        O.apgd_bookkeep(st, i, x_i, g_i, loss, avg_acc, np.zeros((B, 1), np.int64), checks.get(i, 0))
+        xa, gr = t(x_i), t(g_i)
+        mods.ops.apgd_bookkeep(t(correct, torch.int32), t(valid, torch.int32), t(loss), acc, lb, lbl,
+                               red, step, ls, i, checks.get(i, 0), HW, False, flags, done)
+        jobs = [(xba, xa, flags[0], None), (xb, xa, flags[1], None), (gb, gr, flags[1], None)]
+        if i in checks:
+            jobs += [(xa, xb, flags[2], flags[1]), (gr, gb, flags[2], flags[1])]
+        mods.ops.row_select(jobs, B, dev())
+        for name, d_, o_ in (("acc", acc, st.acc), ("loss_best", lb, st.loss_best), ("step", step, st.step),
+                             ("x_best", xb, st.x_best), ("x_best_adv", xba, st.x_best_adv),
+                             ("grad_best", gb, st.grad_best), ("x_adv", xa, st.x_adv), ("grad", gr, st.grad)):
+            assert np.array_equal(d_.cpu().numpy(), o_), (i, name)
+    assert (st.step < np.float32(2 * 8 / 255)).any()  # the schedule did halve something
+    # early stop: once every accuracy is 0 the state freezes
+    acc.zero_()
+    before = lb.clone()
+    z32 = torch.zeros(B, dtype=torch.int32, device=dev())
+    full = torch.full((B,), HW, dtype=torch.int32, device=dev())
+    mods.ops.apgd_bookkeep(z32, full, lb + 1, acc, lb, lbl, red, step, ls, n_iter - 1, 0, HW, True, flags, done)
+    assert int(done) == 1 and torch.equal(lb, before + 1)
+    mods.ops.apgd_bookkeep(z32, full, lb + 5, acc, lb, lbl, red, step, ls, n_iter - 1, 0, HW, True, flags, done)
+    assert torch.equal(lb, before + 1) and int(flags.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("C,skew", [(9, False), (21, True), (151, False), (230, True)])
+def test_pixel_hist_vs_oracle(mods, C, skew):
+    g = torch.Generator().manual_seed(C)
+    n, H, W = 3, 67, 53
+    tgt = torch.randint(0, C, (n, H, W), generator=g)
+    if skew:  # 80 % one class: stresses the warp-aggregated atomics
+        tgt = torch.where(torch.rand(n, H, W, generator=g) < 0.8, torch.full_like(tgt, 3), tgt)
+    pred = torch.where(torch.rand(n, H, W, generator=g) < 0.6, tgt, torch.randint(0, C, (n, H, W), generator=g))
+    tgt = torch.where(torch.rand(n, H, W, generator=g) < 0.1, torch.full_like(tgt, -1), tgt)
+    ref = O.pixel_hist(pred.numpy(), tgt.numpy(), C)
+    out = mods.ops.pixel_hist(pred.to(dev()), tgt.to(dev()), C, want_hist=True)
+    for k in ("hist", "inter", "tgt", "prd"):
+        assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
+    out2 = mods.ops.pixel_hist(pred.to(dev()), tgt.to(dev()), C)  # counters-only kernel
+    for k in ("inter", "tgt", "prd"):
+        assert np.array_equal(out2[k].cpu().numpy(), ref[k]), k
+
+
+def test_metrics_and_compute_iou_acc_vs_reference(mods, golden):
+    g = golden("metrics")
+    C = int(g["C"])
+    pred, target = torch.from_numpy(g["pred"]).to(dev()), torch.from_numpy(g["target"]).to(dev())
+    m_acc, a_acc, m_iou = mods.attacker.compute_iou_acc(pred.clone(), target, C)
+    assert float(m_acc) == float(g["m_acc"]) and float(a_acc) == float(g["a_acc"])
+    assert float(m_iou) == float(g["m_iou"])
+    met = mods.metrics.Metrics(C, -1, dev())
+    met.update(torch.from_numpy(g["logits"]).to(dev()), target)
+    assert np.array_equal(met.hist.cpu().numpy(), g["hist_after_logits"])
+    met.update(torch.nn.functional.one_hot(pred, C).permute(0, 3, 1, 2).float(), target)
+    assert np.array_equal(met.hist.cpu().numpy(), g["hist"])
+    ious, miou = met.compute_iou()
+    f1, mf1 = met.compute_f1()
+    acc, macc, aacc = met.compute_pixel_acc()
+    np.testing.assert_array_equal(np.array(ious), g["ious"])
+    np.testing.assert_array_equal(np.array(f1), g["f1"])
+    np.testing.assert_array_equal(np.array(acc), g["acc"])
+    assert (miou, mf1, macc) == (float(g["miou"]), float(g["mf1"]), float(g["macc"]))
+    assert np.float32(aacc) == g["aacc"]
+
+
+def test_evalsea_vs_reference(mods, golden, tmp_path):
+    g = golden("sea")
+    C = int(g["C"])
+    target = torch.from_numpy(g["target"])
+    l_outs = [torch.from_numpy(a) for a in g["l_outs"]]
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return target.shape[0]
+
+        def __getitem__(self, i):
+            return torch.zeros(1), target[i], str(i)
+
+    (tmp_path / "test_results").mkdir()
+    sd = {}
+    ev = mods.worse.evalSEA(DS(), l_outs, 8, C, "x", str(tmp_path), sd, "m", device=dev())
+    ev.worse_case_eval(bs=int(g["bs"]))
+    assert sd["worst_Acc"] == float(g["worst_Acc"])  # bit-exact
+    assert np.array_equal(sd["worst_Acc_indiv"].numpy(), g["worst_Acc_indiv"])
+    random.seed(225)
+    ev.worst_case_miou()
+    assert sd["final_miou"] == float(g["final_miou"])  # bit-exact python double
+    stats = torch.load(tmp_path / "test_results" / "stats_x_8.pt")
+    assert np.array_equal(stats["run_int_imwise"].numpy(), g["cons_ints"])
+    assert np.array_equal(stats["run_union_imwise"].numpy(), g["cons_unions"])
+
+
+def _tiny(mods, g):
+    m = mods.consumers.TinySegNet(int(g["C"]))
+    sd = {k[2:].replace("_", ".", 1): torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")}
+    m.load_state_dict(sd)
+    return m.to(dev()).eval()
+
+
+class _Rec(torch.nn.Module):
+    def __init__(self, m):
+        super().__init__()
+        self.m, self.inputs = m, []
+
+    def forward(self, x):
+        self.inputs.append(x.detach().clone())
+        return self.m(x)
+
+
+@pytest.mark.parametrize("tag,kind", [("maskce", "mask-ce-avg"), ("maskbal_ign", "mask-ce-bal"), ("js", "js-avg")])
+def test_apgd_largereps_vs_reference_run(mods, golden, tag, kind):
+    """End to end through the drop-in API against the reference's own CPU run (golden):
+    identical RNG stream, tiny conv consumer.  cuDNN and the CPU conv round differently, so
+    sign(grad) may flip where |grad| ~ 0: a small fraction of elements may differ, the
+    metrics (per-image accuracy) must agree to within a pixel or two."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("apgd_" + tag)
+    rec = _Rec(_tiny(mods, g)).eval()
+    x, y, w = (torch.from_numpy(g[n]) for n in ("x", "y", "weights"))
+    torch.manual_seed(1000 + int(g["seed"]))
+    noise_dev = []
+
+    real_rand_like = torch.rand_like
+    it = iter(g["noise"])
+
+    def fake_rand_like(t, *a, **k):  # same uniform draws as the reference's CPU generator
+        return ((torch.from_numpy(next(it)) + 1) / 2).to(t.device)
+
+    torch.rand_like = fake_rand_like
+    try:
+        x_adv, _, acc = mods.attacker.apgd_largereps(
+            rec, x.to(dev()), y.to(dev()), w.to(dev()), norm="Linf", eps=float(g["eps"]),
+            n_iter=int(g["n_iter"]), loss=kind, track_loss="ce-avg", use_rs=True, early_stop=True,
+            num_classes=int(g["C"]))
+    finally:
+        torch.rand_like = real_rand_like
+    assert len(rec.inputs) == len(g["trace"])
+    tr = torch.stack(rec.inputs).cpu().numpy()
+    bad = [(np.abs(tr[i] - g["trace"][i]) > 1e-6).mean() for i in range(len(tr))]
+    assert bad[0] <= 1e-3 and max(bad) <= 0.08, bad
+    P = g["y"][0].size
+    assert np.abs(acc.cpu().numpy() - g["acc"]).max() <= 3.0 / P
+    assert float((x_adv.cpu() - x).abs().max()) <= float(g["eps"]) + 1e-6
+    del noise_dev
+
+
+def test_apgd_train_vs_oracle_same_device_model(mods, golden):
+    """apgd_train on the GPU vs the oracle driving the SAME weights on the CPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden("apgd_train40")
+    model = _tiny(mods, g)
+    x, y, w = (torch.from_numpy(g[n]) for n in ("x", "y", "weights"))
+    x_init = O.random_start(g["x"], float(g["eps"]), g["noise"])
+    xb, acc, lb, xba = mods.attacker.apgd_train(
+        model, x.to(dev()), y.to(dev()), "Linf", float(g["eps"]), n_iter=40, use_rs=False,
+        loss="mask-ce-avg", track_loss="ce-avg", x_init=torch.from_numpy(x_init).to(dev()),
+        num_classes=int(g["C"]), weights=w.to(dev()))
+    P = g["y"][0].size
+    assert np.abs(acc.cpu().numpy() - g["acc"]).max() <= 3.0 / P
+    np.testing.assert_allclose(lb.cpu().numpy(), g["loss_best"], rtol=2e-2)
+    assert (np.abs(xba.cpu().numpy() - g["x_best_adv"]) > 1e-6).mean() <= 0.08
+    assert (np.abs(xb.cpu().numpy() - g["x_best"]) > 1e-6).mean() <= 0.08
+
+
+@pytest.mark.parametrize("tag,cls,los", [("pgd1_pgd", "Pgd_Attack_1", "pgd"), ("pgd_maskce", "Pgd_Attack", "mask-ce-avg"),
+                                         ("pgd_js", "Pgd_Attack", "js-avg")])
+def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden(tag)
+    model = _tiny(mods, g)
+    x, y = torch.from_numpy(g["x"]).to(dev()), torch.from_numpy(g["y"]).to(dev())
+    atk = getattr(mods.val, cls)(epsilon=float(g["eps"]), alpha=float(g["alpha"]), num_iter=int(g["num_iter"]), los=los)
+    if cls == "Pgd_Attack_1":
+        d0 = torch.from_numpy(g["delta0"]).to(dev())
+        real = torch.Tensor.uniform_
+        torch.Tensor.uniform_ = lambda self, *a, **k: self.copy_(d0)
+        try:
+            x_adv = atk.adv_attack(model, x, y)[0]
+        finally:
+            torch.Tensor.uniform_ = real
+    else:
+        x_adv = atk.adv_attack(model, x, y)[0]
+    assert (np.abs(x_adv.cpu().numpy() - g["x_adv"]) > 1e-6).mean() <= 0.03
+    assert float((x_adv - x).abs().max()) <= float(g["eps"]) + 1e-6
+    # parameter gradients were accumulated (loss.backward() semantics)
+    assert all(p.grad is not None for p in model.parameters())
+    model.zero_grad(set_to_none=True)
+    atk2 = getattr(mods.val, cls)(epsilon=float(g["eps"]), num_iter=1, los=los, input_grad_only=True)
+    atk2.adv_attack(model, x, y)
+    assert all(p.grad is None for p in model.parameters())
+
+
+def test_custom_ops_registered(mods):
+    mods.ops.register_custom_ops()
+    z, y, w = make_problem(1, 21, 16, 16, 5)
+    z, y, w = z.to(dev()), y.to(dev()), w.to(dev())
+    d, li, tr, co, va, pr = torch.ops.robseg.loss_fwd_bwd(z, y, w, "mask-ce-bal", -1)
+    ref = mods.ops.loss_fwd_bwd(z, y, "mask-ce-bal", w, want_pred=True)
+    assert torch.equal(d, ref.dlogits) and torch.equal(pr, ref.pred) and torch.equal(li, ref.loss_img)
+    h = torch.ops.robseg.pixel_hist(pr, y, 21, -1)
+    assert int(h.sum()) == int((y != -1).sum())
+
+
+def test_eval_performance_and_cross_entropy(mods):
+    C = 21
+    model = mods.consumers.TinySegNet(C, seed=3).to(dev()).eval()
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for _ in range(2):
+        x = torch.rand(2, 3, 24, 24, generator=g)
+        y = torch.randint(0, C, (2, 24, 24), generator=g)
+        y[0, :3] = -1
+        batches.append((x, y, "n"))
+    stats, l_out = mods.infer.eval_performance(model, batches, n_cls=C)
+    preds = torch.cat([model(b[0].to(dev())).argmax(1).cpu() for b in batches])
+    tg = torch.cat([b[1] for b in batches])
+    preds[tg == -1] = -1
+    assert torch.equal(l_out, preds)
+    h = O.pixel_hist(preds.numpy(), tg.numpy(), C)
+    m_acc, a_acc, m_iou = O.iou_acc_from_counts(h["inter"].sum(0), h["tgt"].sum(0), h["prd"].sum(0))
+    assert abs(stats["aAcc"] - float(a_acc)) < 1e-7 and abs(stats["mIoU"] - float(m_iou)) < 1e-6
+    # CrossEntropy module (semseg/losses.py:6-27) vs torch, forward and backward
+    z = torch.randn(2, C, 24, 24, generator=g).to(dev()).requires_grad_()
+    y = batches[0][1].to(dev())
+    w = (0.5 + torch.rand(C, generator=g)).to(dev())
+    for weight in (None, w):
+        ours = mods.losses.CrossEntropy(-1, weight)(z, y)
+        ref = torch.nn.functional.cross_entropy(z, y, weight=weight, ignore_index=-1)
+        assert torch.allclose(ours, ref, rtol=1e-5)
+        (g1,) = torch.autograd.grad(ours, [z])
+        (g2,) = torch.autograd.grad(ref, [z])
+        assert rel(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5

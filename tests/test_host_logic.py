@@ -1,0 +1,171 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every declared
+symbol (no compute calls), the worst-case aggregation host code is bit-exact against the
+reference's golden run and against the oracle, the data-independent APGD schedule, the
+image-shard plumbing and its world-size-2 gloo all-reduce, and the no-CPU-fallback rule."""
+import os
+import random
+import re
+import statistics
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import robseg_oracle as O
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    from importlib import import_module
+
+    names = dict(lib="._lib", ops=".ops", attacker=".semseg.attacker", worse=".tools.worse_only",
+                 dist=".dist", consumers=".consumers", val=".semseg.val", metrics=".semseg.metrics")
+    return type("M", (), {k: import_module("robseg_b200" + v) for k, v in names.items()})
+
+
+def test_library_exports_every_declared_symbol(mods):
+    import __graft_entry__ as ge
+
+    if not os.path.isfile(mods.lib.LIB_PATH):
+        ge.build()
+    header = open(os.path.join(ROOT, "include", "robseg_b200.h")).read()
+    declared = set(re.findall(r"\b(robseg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"robseg_stream_t"}
+    assert declared == set(mods.lib.SIGNATURES), declared ^ set(mods.lib.SIGNATURES)
+    lib = mods.lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.robseg_version() == mods.lib.ABI_VERSION
+    assert lib.robseg_loss_workspace_bytes(16, 150, 512 * 512, 0) == 16 * (512 * 512 // 32) * 16
+    syms = subprocess.run(["nm", "-D", "--defined-only", mods.lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (robseg_[a-z0-9_]+)", syms))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_with_tma(mods):
+    sass = subprocess.run(["cuobjdump", "-sass", mods.lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTMALDG" in sass  # the loss kernel's tensor-map bulk loads
+
+
+def test_no_cpu_fallback(mods):
+    z = torch.randn(1, 5, 4, 4)
+    y = torch.randint(0, 5, (1, 4, 4))
+    with pytest.raises(RuntimeError):
+        mods.ops.loss_fwd_bwd(z, y, "ce")
+    with pytest.raises(RuntimeError):
+        mods.attacker.apgd_train(mods.consumers.TinySegNet(5).eval(), torch.rand(1, 3, 4, 4), y, "Linf", 0.03)
+    with pytest.raises(NotImplementedError):
+        mods.attacker.apgd_train(mods.consumers.TinySegNet(5).eval(), torch.rand(1, 3, 4, 4), y, "L2", 0.03)
+    # the product never imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "robust-segmentation_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "robseg_oracle" not in src and "oracle" not in src.replace("oracle/", ""), f
+
+
+def test_exact_mean_matches_statistics_mean(mods):
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(1, 200))
+        v = rng.random(n) * 10.0 ** rng.integers(-12, 3, n)
+        if rng.random() < 0.3:
+            v[rng.integers(0, n)] = 0.0
+        assert mods.worse.exact_mean(v) == statistics.mean(v.tolist())
+
+
+def test_greedy_worst_miou_bit_exact(mods, golden):
+    g = golden("sea")
+    random.seed(225)
+    final, sel = mods.worse.greedy_worst_miou(g["cons_ints"], g["cons_unions"])
+    assert final == float(g["final_miou"])
+    # and against the oracle's pure-python replay on a different random problem
+    rng = np.random.default_rng(3)
+    A, N, C = 3, 12, 7
+    tgt = rng.integers(1, 50, (1, N, C))
+    inter = np.minimum(rng.integers(0, 50, (A, N, C)), tgt)
+    union = tgt + rng.integers(0, 30, (A, N, C))
+    r1, r2 = random.Random(5), random.Random(5)
+    f1, s1 = mods.worse.greedy_worst_miou(inter, union, rng=r1)
+    f2, s2 = O.sea_worst_miou(inter, union, rng=r2)
+    assert f1 == f2 and s1 == s2
+
+
+def test_schedule_is_data_independent(mods):
+    for n in (1, 3, 4, 10, 90, 120, 300):
+        assert mods.attacker.apgd_schedule(n) == dict(O.apgd_schedule(n))
+    assert mods.attacker.apgd_schedule(120)[25] == 26
+
+
+def test_shard_ranges_cover(mods):
+    for n, w in ((2000, 8), (17, 4), (3, 8), (16, 1)):
+        spans = [mods.dist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_signature_parity_with_reference_surface(mods):
+    """Names, positional order and defaults of SURVEY.md section 8b."""
+    import inspect
+
+    a = mods.attacker
+    sig = inspect.signature(a.apgd_largereps)
+    assert list(sig.parameters)[:4] == ["model", "x", "y", "weights"]
+    assert sig.parameters["eps"].default == 8.0 / 255.0 and sig.parameters["n_iter"].default == 10
+    assert sig.parameters["loss"].default == "ce" and sig.parameters["num_classes"].default == 21
+    sig = inspect.signature(a.apgd_train)
+    assert list(sig.parameters) == ["model", "x", "y", "norm", "eps", "n_iter", "use_rs", "loss", "verbose",
+                                    "is_train", "early_stop", "track_loss", "logger", "y_target",
+                                    "ignore_index", "x_init", "num_classes", "weights"]
+    assert set(a.criterion_dict) == {"ce", "ce-avg", "mask-ce-avg", "mask-ce-bal", "js-avg"}
+    assert list(inspect.signature(a.compute_iou_acc).parameters) == [
+        "pred", "target", "n_cls", "verbose", "ignore_index", "device"]
+    p = mods.val.Pgd_Attack(epsilon=2 / 255)  # the trainer's spelling
+    assert p.epsilon == 2 / 255 and mods.val.Pgd_Attack(eps=1 / 255).epsilon == 1 / 255
+    assert mods.val.Pgd_Attack_1(epsilon=3 / 255).epsilon == 3 / 255
+    m = inspect.signature(mods.metrics.Metrics.__init__)
+    assert list(m.parameters)[1:] == ["num_classes", "ignore_label", "device"]
+    sea = inspect.signature(mods.worse.evalSEA.__init__)
+    assert list(sea.parameters)[1:9] == ["val_data", "l_outs", "eps", "n_cls", "addendum", "saveDir",
+                                         "saveDict", "modelName"]
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+ge.load_package()
+from importlib import import_module
+D = import_module("robseg_b200.dist")
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+A, N, C = 3, 11, 5
+g = torch.Generator().manual_seed(0)
+inter = torch.randint(0, 100, (A, N, C), generator=g)
+tgt = inter + torch.randint(0, 50, (A, N, C), generator=g)
+prd = inter + torch.randint(0, 50, (A, N, C), generator=g)
+hist = torch.randint(0, 9, (A, C, C), generator=g)
+lo, hi = D.shard_range(N, rank, world)
+gi, gt, gp, gh = D.allreduce_counters(N, lo, inter[:, lo:hi], tgt[:, lo:hi], prd[:, lo:hi], hist)
+assert torch.equal(gi, inter) and torch.equal(gt, tgt) and torch.equal(gp, prd)
+assert torch.equal(gh, hist * world)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_allreduce_counters_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
