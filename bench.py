@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
     return ap.parse_args()
 
 
@@ -477,6 +478,10 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.debug_stack:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(a.debug_stack, repeat=True, file=sys.stderr)
     if a.impl == "reference":
         run_reference(a)
     else:

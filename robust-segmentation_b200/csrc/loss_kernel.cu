@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -43,7 +44,7 @@ struct LossParams {
   float4* partials;
   int64_t HW;
   int kind, ignore_index, B, C;
-  int tiles_per_img, num_tiles, n_stages, n_consumers;
+  int tiles_per_img, num_tiles, n_slots, n_consumers;
   float inv_hw;
 };
 
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(512, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
                                              ~static_cast<uintptr_t>(127));
   constexpr int ROW = 32 * VEC;
-  const int S = p.n_stages, W = p.n_consumers;
+  const int W = p.n_consumers, K = p.n_slots, S = W * K;
   const uint32_t stage_bytes = (uint32_t)p.C * ROW * sizeof(T);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + S;
@@ -390,33 +391,37 @@ __global__ void __launch_bounds__(512, 1)
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      int s = 0;
+      // ring item `it` -> consumer (it % W), that consumer's private slot ((it / W) % K).
+      // A stage is only ever consumed by ONE warp, so its mbarrier phases are observed in
+      // order by a single waiter (a parity wait is ambiguous for a waiter two phases away).
+      int w = 0, k = 0;
       uint32_t round = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int s = w * K + k;
         mbar_wait(empty + s, (round & 1u) ^ 1u);
         mbar_arrive_expect_tx(full + s, stage_bytes);
         const int b = tile / p.tiles_per_img;
         const int px0 = (tile - b * p.tiles_per_img) * ROW;
         tma_load_3d(smem + (size_t)s * stage_bytes, &tmap, px0, 0, b, full + s);
-        if (++s == S) s = 0, ++round;
+        if (++w == W) {
+          w = 0;
+          if (++k == K) k = 0, ++round;
+        }
       }
     }
-  } else {  // ===== consumers: ring item `it` -> warp (it % W) =====
+  } else {  // ===== consumers =====
     const int w = warp - 1;
-    int it = w;
-    int s = w % S;
-    uint32_t round = w / S;
+    int k = 0;
+    uint32_t round = 0;
     for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles; tile += W * gridDim.x) {
+      const int s = w * K + k;
       mbar_wait(full + s, round & 1u);
       process_tile<T, VEC>(p, reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes), tile,
                            lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
-      it += W;
-      s += W;
-      while (s >= S) s -= S, ++round;
+      if (++k == K) k = 0, ++round;
     }
-    (void)it;
   }
 }
 
@@ -504,12 +509,16 @@ static int launch_tma(const LossParams& p0, cudaStream_t stream) {
   p.tiles_per_img = (int)((p.HW + ROW - 1) / ROW);
   p.num_tiles = p.B * p.tiles_per_img;
   const size_t stage = (size_t)p.C * ROW * sizeof(T);
-  int S = (int)((kSmemBudget - 512) / stage);
-  if (S > 32) S = 32;
-  int W = S - (S >= 8 ? S / 4 : 1);
+  // W consumer warps, each with K private stages (K-deep prefetch); W*K stages must fit.
+  const int s_max = (int)((kSmemBudget - 512) / stage);
+  int K = s_max >= 16 ? 2 : 1;
+  if (const char* e = getenv("ROBSEG_LOSS_SLOTS")) K = atoi(e) > 0 ? atoi(e) : K;
+  if (K > s_max) K = s_max;
+  int W = s_max / K;
   if (W > 15) W = 15;
-  if (W < 1) W = 1;
-  p.n_stages = S, p.n_consumers = W;
+  if (const char* e = getenv("ROBSEG_LOSS_WARPS")) W = atoi(e) > 0 && atoi(e) <= W ? atoi(e) : W;
+  const int S = W * K;
+  p.n_slots = K, p.n_consumers = W;
   const size_t smem = S * stage + 2 * S * sizeof(uint64_t) + 128;
 
   CUtensorMap tmap;

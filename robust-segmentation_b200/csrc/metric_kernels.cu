@@ -86,6 +86,39 @@ __global__ void __launch_bounds__(kHistThreads)
   }
 }
 
+// Fallback for class counts whose [C,C] tile does not fit in shared memory: warp-aggregated
+// atomics straight to the global per-image histogram.
+__global__ void __launch_bounds__(kHistThreads)
+    pixel_hist_global_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ labels,
+                             int n_lab_img, int64_t HW, int C, int ignore_index,
+                             unsigned long long* hist, unsigned long long* hist_total) {
+  const int img = blockIdx.y;
+  const int64_t* pp = pred + (int64_t)img * HW;
+  const int64_t* lp = labels + (int64_t)(img % n_lab_img) * HW;
+  const int64_t p0 = (int64_t)blockIdx.x * kPxPerBlock;
+  int64_t p1 = p0 + kPxPerBlock;
+  if (p1 > HW) p1 = HW;
+  for (int64_t base = p0 + (threadIdx.x & ~31); base < p1; base += kHistThreads) {
+    const int64_t i = base + (threadIdx.x & 31);
+    int t = -1, q = -1;
+    if (i < p1) {
+      const int64_t tv = __ldcs(lp + i), qv = __ldcs(pp + i);
+      t = (tv != ignore_index && tv >= 0 && tv < C) ? (int)tv : -1;
+      q = (qv >= 0 && qv < C) ? (int)qv : -1;
+    }
+    const bool active = t >= 0 && q >= 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) continue;
+    const int key = t * C + q;
+    const unsigned peers = __match_any_sync(mask, key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      const unsigned long long n = (unsigned long long)__popc(peers);
+      if (hist) atomicAdd(hist + (int64_t)img * C * C + key, n);
+      if (hist_total) atomicAdd(hist_total + key, n);
+    }
+  }
+}
+
 // acc[a,n] = sum_c inter / sum_c tgt (fp32 division of exactly represented sums),
 // worst[n] = min over attacks.  One thread per image.
 __global__ void __launch_bounds__(256)
@@ -122,11 +155,21 @@ extern "C" int robseg_pixel_hist(const int64_t* pred, const int64_t* labels, int
                  "bad shape n_img=%d HW=%lld C=%d", n_img, (long long)HW, C);
   ROBSEG_REQUIRE(hist || hist_total || inter || tgt || prd, "no output requested");
   const bool full = hist != nullptr || hist_total != nullptr;
-  const size_t smem = (full ? (size_t)C * C : (size_t)3 * C) * sizeof(int);
-  ROBSEG_REQUIRE(smem <= 200 * 1024, "C=%d too large for the shared-memory confusion tile", C);
+  size_t smem = (full ? (size_t)C * C : (size_t)3 * C) * sizeof(int);
+  ROBSEG_REQUIRE((size_t)3 * C * sizeof(int) <= 200 * 1024, "C=%d too large", C);
   dim3 grid((unsigned)((HW + kPxPerBlock - 1) / kPxPerBlock), n_img);
   auto u = [](int64_t* q) { return reinterpret_cast<unsigned long long*>(q); };
-  if (full) {
+  if (full && smem > 200 * 1024) {
+    // [C,C] tile does not fit: histogram through global atomics, counters through the 3C kernel
+    pixel_hist_global_kernel<<<grid, kHistThreads, 0, stream>>>(pred, labels, n_lab_img, HW, C,
+                                                                ignore_index, u(hist), u(hist_total));
+    ROBSEG_LAUNCH_CHECK();
+    if (inter || tgt || prd) {
+      smem = (size_t)3 * C * sizeof(int);
+      pixel_hist_kernel<false><<<grid, kHistThreads, smem, stream>>>(
+          pred, labels, n_lab_img, HW, C, ignore_index, nullptr, nullptr, u(inter), u(tgt), u(prd));
+    }
+  } else if (full) {
     ROBSEG_CUDA(cudaFuncSetAttribute(pixel_hist_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pixel_hist_kernel<true><<<grid, kHistThreads, smem, stream>>>(

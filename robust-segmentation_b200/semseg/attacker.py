@@ -230,7 +230,10 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     n_cls = logits.shape[1]
     del logits
     grad = grad.contiguous()
-    acc = out.correct.float() / n_pxl  # ignored pixels count as wrong here (:370-371)
+    # ignored pixels count as wrong here (:370-371).  Tensor / tensor is an IEEE division on
+    # the device (tensor / python-scalar would multiply by a rounded reciprocal), matching
+    # the bookkeeping kernel and the reference's CPU mean.
+    acc = out.correct.float() / torch.full((), float(n_pxl), device=device)
     loss_best = track.clone()
     loss_best_last = loss_best.clone()
     reduced_last = torch.ones_like(loss_best)
