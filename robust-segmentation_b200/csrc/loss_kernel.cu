@@ -125,20 +125,44 @@ struct Vec<__nv_bfloat16, VEC> {
 };
 
 // ---- one warp tile -------------------------------------------------------------------------
-// tile: shared memory [C][32*VEC] of T, already filled (zeros beyond HW).
-template <typename T, int VEC>
+// tile: shared memory [C][32*VEC] of T, already filled (zeros beyond HW).  G warps share the
+// tile, warp `half` walks channels [c_lo, c_hi) and the partial max / sum-exp / first-max
+// index are combined through `xch` (shared) with a named barrier; G == 1: one warp, no exchange.
+struct PairXch {  // per stage group, G == 2 only
+  float* fmax;    // [2][ROW]
+  float* fsum;    // [2][ROW]
+  int* idx;       // [2][ROW]
+  int bar_id;
+};
+
+__device__ __forceinline__ void pair_sync(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // SASS FMNMX3
+  return r;
+}
+
+template <typename T, int VEC, int G, bool PARTIAL>
 __device__ __forceinline__ void process_tile(const LossParams& p, const T* __restrict__ tile,
-                                             int tile_idx, int lane) {
+                                             int tile_idx, int lane, int half,
+                                             const PairXch& xch) {
   constexpr int ROW = 32 * VEC;
   constexpr int NACC = (VEC >= 4) ? 1 : 4 / VEC;  // independent accumulator sets per pixel
   constexpr int UNR = 8;
+  constexpr int kNone = 0x7fffffff;
   using V = Vec<T, VEC>;
   const int C = p.C;
+  const int c_lo = (G == 1) ? 0 : half * ((C + 1) >> 1);
+  const int c_hi = (G == 1) ? C : (half == 0 ? ((C + 1) >> 1) : C);
   const int b = tile_idx / p.tiles_per_img;
   const int64_t px = (int64_t)(tile_idx - b * p.tiles_per_img) * ROW + lane * VEC;
-  const bool inb = px < p.HW;  // HW % VEC == 0 on the vector path, so a lane is all in or out
+  const bool inb = PARTIAL ? (px < p.HW) : true;  // HW % VEC == 0: a lane is all in or all out
   const int64_t pix = (int64_t)b * p.HW + px;
   const T* col = tile + lane * VEC;
+  const bool argmax_only = p.kind == ROBSEG_LOSS_ARGMAX;
 
   // labels: issued now, consumed after pass 1
   int y[VEC];
@@ -158,80 +182,122 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
     for (int j = 0; j < VEC; ++j) y[j] = p.ignore_index;
   }
 
-  // ---- pass 1: max and argmax (lowest index on ties, as Tensor.max(1)) -------------------
-  float m[NACC][VEC];
-  int am[NACC][VEC];
-#pragma unroll
-  for (int a = 0; a < NACC; ++a)
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) m[a][j] = -INFINITY, am[a][j] = 0;
-  int c = 0;
-#pragma unroll 1
-  for (; c + UNR <= C; c += UNR) {
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      float v[VEC];
-      V::lds(col + (c + u) * ROW, v);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const bool g = v[j] > m[u % NACC][j];
-        m[u % NACC][j] = g ? v[j] : m[u % NACC][j];
-        am[u % NACC][j] = g ? (c + u) : am[u % NACC][j];
-      }
-    }
-  }
-#pragma unroll 1
-  for (; c < C; ++c) {
-    float v[VEC];
-    V::lds(col + c * ROW, v);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      // the tail always follows full groups, so set 0 still sees ascending indices
-      const bool g = v[j] > m[0][j] || (v[j] == m[0][j] && c < am[0][j]);
-      m[0][j] = g ? v[j] : m[0][j];
-      am[0][j] = g ? c : am[0][j];
-    }
-  }
+  // ---- pass 1: channel max.  ARGMAX-only launches also track the index here (one pass);
+  // loss launches find the first maximal channel by equality during pass 2.
   float mx[VEC];
   int amx[VEC];
+  if (argmax_only) {
+    float m[NACC][VEC];
+    int am[NACC][VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    mx[j] = m[0][j], amx[j] = am[0][j];
+    for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int a = 1; a < NACC; ++a) {
-      const bool g = m[a][j] > mx[j] || (m[a][j] == mx[j] && am[a][j] < amx[j]);
-      mx[j] = g ? m[a][j] : mx[j];
-      amx[j] = g ? am[a][j] : amx[j];
+      for (int j = 0; j < VEC; ++j) m[a][j] = -INFINITY, am[a][j] = c_lo;
+    int c = c_lo;
+#pragma unroll 1
+    for (; c + UNR <= c_hi; c += UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float v[VEC];
+        V::lds(col + (c + u) * ROW, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const bool g = v[j] > m[u % NACC][j];
+          m[u % NACC][j] = g ? v[j] : m[u % NACC][j];
+          am[u % NACC][j] = g ? (c + u) : am[u % NACC][j];
+        }
+      }
+    }
+#pragma unroll 1
+    for (; c < c_hi; ++c) {
+      float v[VEC];
+      V::lds(col + c * ROW, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const bool g = v[j] > m[0][j] || (v[j] == m[0][j] && c < am[0][j]);
+        m[0][j] = g ? v[j] : m[0][j];
+        am[0][j] = g ? c : am[0][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      mx[j] = m[0][j], amx[j] = am[0][j];
+#pragma unroll
+      for (int a = 1; a < NACC; ++a) {
+        const bool g = m[a][j] > mx[j] || (m[a][j] == mx[j] && am[a][j] < amx[j]);
+        mx[j] = g ? m[a][j] : mx[j];
+        amx[j] = g ? am[a][j] : amx[j];
+      }
+    }
+  } else {
+    float m[NACC][VEC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) m[a][j] = -INFINITY;
+    int c = c_lo;
+#pragma unroll 1
+    for (; c + UNR <= c_hi; c += UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; u += 2) {
+        float v0[VEC], v1[VEC];
+        V::lds(col + (c + u) * ROW, v0);
+        V::lds(col + (c + u + 1) * ROW, v1);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          m[(u / 2) % NACC][j] = fmax3(m[(u / 2) % NACC][j], v0[j], v1[j]);
+      }
+    }
+#pragma unroll 1
+    for (; c < c_hi; ++c) {
+      float v[VEC];
+      V::lds(col + c * ROW, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) m[0][j] = fmaxf(m[0][j], v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      mx[j] = m[0][j];
+#pragma unroll
+      for (int a = 1; a < NACC; ++a) mx[j] = fmaxf(mx[j], m[a][j]);
+      amx[j] = kNone;
     }
   }
-
-  bool valid[VEC], hit[VEC];
-  int ys[VEC];
-  int n_correct = 0, n_valid = 0;
+  if constexpr (G == 2) {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
-    hit[j] = valid[j] && (amx[j] == y[j]);
-    ys[j] = valid[j] ? y[j] : 0;
-    n_correct += hit[j];
-    n_valid += valid[j];
-  }
-  if (p.pred != nullptr && inb) {
-    if constexpr (VEC == 1) {
-      p.pred[pix] = amx[0];
-    } else {
-      longlong2* pp = reinterpret_cast<longlong2*>(p.pred + pix);
+    for (int j = 0; j < VEC; ++j) {
+      xch.fmax[half * ROW + lane * VEC + j] = mx[j];
+      xch.idx[half * ROW + lane * VEC + j] = amx[j];
+    }
+    pair_sync(xch.bar_id);
 #pragma unroll
-      for (int j = 0; j < VEC / 2; ++j) pp[j] = make_longlong2(amx[2 * j], amx[2 * j + 1]);
+    for (int j = 0; j < VEC; ++j) {
+      const float om = xch.fmax[(half ^ 1) * ROW + lane * VEC + j];
+      const int oi = xch.idx[(half ^ 1) * ROW + lane * VEC + j];
+      // ties between the halves go to the lower half (lower channel indices)
+      const bool take = half == 0 ? (om > mx[j]) : (om >= mx[j]);
+      amx[j] = take ? oi : amx[j];
+      mx[j] = take ? om : mx[j];
     }
   }
 
   float loss_sum = 0.f, ce_sum = 0.f;
-  if (p.kind != ROBSEG_LOSS_ARGMAX) {
-    // ---- pass 2: sum of exp(z - max) ------------------------------------------------------
+  int n_correct = 0, n_valid = 0;
+  bool valid[VEC], hit[VEC];
+  int ys[VEC];
+  if (argmax_only) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+      hit[j] = valid[j] && (amx[j] == y[j]);
+      n_correct += hit[j], n_valid += valid[j];
+    }
+  } else {
+    // ---- pass 2: sum of exp(z - max) + first maximal channel --------------------------------
     // exp(z-m) = 2^(z*log2e - mL) with mL = fl(m*log2e); the rounding residual of that
     // product is common to all channels (cancels in softmax) and is removed from the
-    // log-sum-exp exactly through `resid`.
+    // log-sum-exp exactly through `resid`.  Channels are walked downwards so that the
+    // predicated index write that lands last is the lowest maximal channel.
     float mL[VEC], resid[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -243,23 +309,51 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) s[a][j] = 0.f;
-    c = 0;
+    int c = c_hi;
 #pragma unroll 1
-    for (; c + UNR <= C; c += UNR) {
+    for (; c - UNR >= c_lo; c -= UNR) {
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VEC];
-        V::lds(col + (c + u) * ROW, v);
+        V::lds(col + (c - 1 - u) * ROW, v);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) s[u % NACC][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+        for (int j = 0; j < VEC; ++j) {
+          s[u % NACC][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+          if (v[j] == mx[j]) amx[j] = c - 1 - u;
+        }
       }
     }
 #pragma unroll 1
-    for (; c < C; ++c) {
+    for (; c > c_lo; --c) {
       float v[VEC];
-      V::lds(col + c * ROW, v);
+      V::lds(col + (c - 1) * ROW, v);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+      for (int j = 0; j < VEC; ++j) {
+        s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+        if (v[j] == mx[j]) amx[j] = c - 1;
+      }
+    }
+    float st[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      st[j] = s[0][j];
+#pragma unroll
+      for (int a = 1; a < NACC; ++a) st[j] += s[a][j];
+    }
+    if constexpr (G == 2) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        xch.fsum[half * ROW + lane * VEC + j] = st[j];
+        xch.idx[half * ROW + lane * VEC + j] = amx[j];
+      }
+      pair_sync(xch.bar_id);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float os = xch.fsum[(half ^ 1) * ROW + lane * VEC + j];
+        const int oi = xch.idx[(half ^ 1) * ROW + lane * VEC + j];
+        st[j] = half == 0 ? st[j] + os : os + st[j];  // same order in both warps
+        amx[j] = min(amx[j], oi);
+      }
     }
 
     // ---- per-pixel loss terms ---------------------------------------------------------------
@@ -268,12 +362,13 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
     bool any_grad = false;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float st = s[0][j];
-#pragma unroll
-      for (int a = 1; a < NACC; ++a) st += s[a][j];
+      valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+      hit[j] = valid[j] && (amx[j] == y[j]);
+      ys[j] = valid[j] ? y[j] : 0;
+      n_correct += hit[j], n_valid += valid[j];
       const float zy = V::ld1(col + ys[j] * ROW + j);
-      const float ln_s = logf(st) - resid[j] * kLn2;  // lse - m
-      const float logp = (zy - mx[j]) - ln_s;          // log softmax_y  (<= 0)
+      const float ln_s = logf(st[j]) - resid[j] * kLn2;  // lse - m
+      const float logp = (zy - mx[j]) - ln_s;            // log softmax_y  (<= 0)
       const float ce = valid[j] ? -logp : 0.f;
       float l, coef;
       if (p.kind == ROBSEG_LOSS_CE) {
@@ -295,12 +390,12 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       float gs = g_img;
       if (p.upstream != nullptr && inb) gs *= __ldg(p.upstream + pix + j);
       const float cg = coef * gs;
-      kfac[j] = cg / st;
+      kfac[j] = cg / st[j];
       sub[j] = cg;
       ey[j] = ex2_approx(fmaf(zy, kLog2e, -mL[j]));
       any_grad |= (cg != 0.f);
     }
-    if (p.loss_pix != nullptr && inb) {
+    if (p.loss_pix != nullptr && inb && half == 0) {
       if constexpr (VEC == 1) {
         p.loss_pix[pix] = loss[0];
       } else if constexpr (VEC == 2) {
@@ -315,7 +410,8 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 
     // ---- pass 3: gradient, written straight from registers ---------------------------------
     if (p.dlogits != nullptr) {
-      T* gout = reinterpret_cast<T*>(p.dlogits) + (int64_t)b * C * p.HW + px;
+      T* gp = reinterpret_cast<T*>(p.dlogits) + ((int64_t)b * C + c_lo) * p.HW + px;
+      const int64_t hw = p.HW;
       const bool warp_any = __any_sync(0xffffffffu, any_grad);
       if (!warp_any) {
         // every pixel of the tile is masked out (wrongly classified / ignored): zeros
@@ -324,76 +420,92 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
         for (int j = 0; j < VEC; ++j) zero[j] = 0.f;
         if (inb) {
 #pragma unroll 4
-          for (c = 0; c < C; ++c) V::stg(gout + (int64_t)c * p.HW, zero);
+          for (c = c_lo; c < c_hi; ++c, gp += hw) V::stg(gp, zero);
         }
       } else {
-        c = 0;
+        c = c_lo;
 #pragma unroll 1
-        for (; c + UNR <= C; c += UNR) {
+        for (; c + UNR <= c_hi; c += UNR) {
+          float v[UNR][VEC];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) V::lds(col + (c + u) * ROW, v[u]);
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
-            float v[VEC], g[VEC];
-            V::lds(col + (c + u) * ROW, v);
+            float g[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-              g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
-            if (inb) V::stg(gout + (int64_t)(c + u) * p.HW, g);
+              g[j] = ex2_approx(fmaf(v[u][j], kLog2e, -mL[j])) * kfac[j];
+            if (inb) V::stg(gp, g);
+            gp += hw;
           }
         }
 #pragma unroll 1
-        for (; c < C; ++c) {
+        for (; c < c_hi; ++c, gp += hw) {
           float v[VEC], g[VEC];
           V::lds(col + c * ROW, v);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
-          if (inb) V::stg(gout + (int64_t)c * p.HW, g);
+          if (inb) V::stg(gp, g);
         }
         // the label channel: coef*(p_y - 1).  Same thread, same address, program order.
-        __syncwarp();
+        T* gy = reinterpret_cast<T*>(p.dlogits) + (int64_t)b * C * p.HW + px;
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          if (sub[j] != 0.f)
-            V::st1(gout + (int64_t)ys[j] * p.HW + j, fmaf(ey[j], kfac[j], -sub[j]));
+          if (sub[j] != 0.f && ys[j] >= c_lo && ys[j] < c_hi)
+            V::st1(gy + (int64_t)ys[j] * p.HW + j, fmaf(ey[j], kfac[j], -sub[j]));
       }
     }
   }
 
-  // ---- per-tile partials (fixed shuffle order -> deterministic) ----------------------------
-  loss_sum = warp_sum(loss_sum);
-  ce_sum = warp_sum(ce_sum);
-  n_correct = warp_sum(n_correct);
-  n_valid = warp_sum(n_valid);
-  if (lane == 0)
-    p.partials[tile_idx] =
-        make_float4(loss_sum, ce_sum, __int_as_float(n_correct), __int_as_float(n_valid));
+  if (half == 0) {
+    if (p.pred != nullptr && inb) {
+      if constexpr (VEC == 1) {
+        p.pred[pix] = amx[0];
+      } else {
+        longlong2* pp = reinterpret_cast<longlong2*>(p.pred + pix);
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) pp[j] = make_longlong2(amx[2 * j], amx[2 * j + 1]);
+      }
+    }
+    // ---- per-tile partials (fixed shuffle order -> deterministic) --------------------------
+    loss_sum = warp_sum(loss_sum);
+    ce_sum = warp_sum(ce_sum);
+    n_correct = warp_sum(n_correct);
+    n_valid = warp_sum(n_valid);
+    if (lane == 0)
+      p.partials[tile_idx] =
+          make_float4(loss_sum, ce_sum, __int_as_float(n_correct), __int_as_float(n_valid));
+  }
 }
 
 // ---- fast path: persistent TMA ring --------------------------------------------------------
-template <typename T, int VEC>
-__global__ void __launch_bounds__(512, 1)
+// Block = 1 producer warp + W*G consumer warps.  Consumer group w (G warps) owns K private
+// stages; ring item `it` goes to group it % W, slot (it / W) % K.  A stage is only ever
+// consumed by one group, so its mbarrier phases are observed in order (a parity wait is
+// ambiguous for a waiter that is two phases away).
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(G == 2 ? 1024 : 512, 1)
     loss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const LossParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                             ~static_cast<uintptr_t>(127));
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // keep the pointer derived from the __shared__ symbol so loads compile to LDS
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   constexpr int ROW = 32 * VEC;
   const int W = p.n_consumers, K = p.n_slots, S = W * K;
   const uint32_t stage_bytes = (uint32_t)p.C * ROW * sizeof(T);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* empty = full + S;
+  float* xbase = reinterpret_cast<float*>(empty + S);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
-    for (int s = 0; s < S; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+    for (int s = 0; s < S; ++s) mbar_init(full + s, 1), mbar_init(empty + s, G);
     mbar_fence_init();
   }
   __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      // ring item `it` -> consumer (it % W), that consumer's private slot ((it / W) % K).
-      // A stage is only ever consumed by ONE warp, so its mbarrier phases are observed in
-      // order by a single waiter (a parity wait is ambiguous for a waiter two phases away).
       int w = 0, k = 0;
       uint32_t round = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -410,14 +522,25 @@ __global__ void __launch_bounds__(512, 1)
       }
     }
   } else {  // ===== consumers =====
-    const int w = warp - 1;
+    const int w = (warp - 1) / G, half = (warp - 1) % G;
+    PairXch xch{};
+    if constexpr (G == 2) {
+      xch.fmax = xbase + (size_t)w * 6 * ROW;
+      xch.fsum = xch.fmax + 2 * ROW;
+      xch.idx = reinterpret_cast<int*>(xch.fsum + 2 * ROW);
+      xch.bar_id = 1 + w;
+    }
     int k = 0;
     uint32_t round = 0;
+    const bool has_partial = (p.HW % ROW) != 0;
     for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles; tile += W * gridDim.x) {
       const int s = w * K + k;
       mbar_wait(full + s, round & 1u);
-      process_tile<T, VEC>(p, reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes), tile,
-                           lane);
+      const T* st = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
+      if (has_partial && (tile % p.tiles_per_img) == p.tiles_per_img - 1)
+        process_tile<T, VEC, G, true>(p, st, tile, lane, half, xch);
+      else
+        process_tile<T, VEC, G, false>(p, st, tile, lane, half, xch);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++k == K) k = 0, ++round;
@@ -441,7 +564,7 @@ __global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
     for (int c = 0; c < p.C; ++c)
       stage[c * 32 + lane] = inb ? src[(int64_t)c * p.HW] : T(0.f);
     __syncwarp();
-    process_tile<T, 1>(p, stage, tile, lane);
+    process_tile<T, 1, 1, true>(p, stage, tile, lane, 0, PairXch{});
     __syncwarp();
   }
 }
@@ -494,32 +617,43 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // ring + barriers + alignment slack
 
 static int pick_vec(int C, int esize) {
-  // widest per-lane vector whose stage ([C][32*VEC] elements) stays <= ~24 KB, so the ring
-  // keeps >= 8 stages; per-lane bytes are capped at 16.
+  // widest per-lane vector whose stage ([C][32*VEC] elements) stays <= 40 KB, so at least 5
+  // consumer warps fit; per-lane bytes are capped at 16.  Wider rows matter: measured on B200
+  // at C=150 the 128 B-row layout tops out near 5.1 TB/s, 256 B rows reach 5.6 TB/s
+  // (profiles/r01_loss_sweep.md).
   const int max_vec = 16 / esize;
   int vec = max_vec;
-  while (vec > (esize == 2 ? 2 : 1) && (size_t)C * 32 * vec * esize > 24 * 1024) vec >>= 1;
+  // bf16 pays an unpack per element, so it keeps the smaller (<= 24 KB, more warps) stages.
+  const size_t cap = esize == 2 ? 24 * 1024 : 40 * 1024;
+  while (vec > (esize == 2 ? 2 : 1) && (size_t)C * 32 * vec * esize > cap) vec >>= 1;
+  if (const char* e = getenv("ROBSEG_LOSS_VEC")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4 || v == 8) && v <= max_vec && v >= (esize == 2 ? 2 : 1)) vec = v;
+  }
   return vec;
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int G>
 static int launch_tma(const LossParams& p0, cudaStream_t stream) {
   LossParams p = p0;
   constexpr int ROW = 32 * VEC;
   p.tiles_per_img = (int)((p.HW + ROW - 1) / ROW);
   p.num_tiles = p.B * p.tiles_per_img;
   const size_t stage = (size_t)p.C * ROW * sizeof(T);
-  // W consumer warps, each with K private stages (K-deep prefetch); W*K stages must fit.
-  const int s_max = (int)((kSmemBudget - 512) / stage);
-  int K = s_max >= 16 ? 2 : 1;
-  if (const char* e = getenv("ROBSEG_LOSS_SLOTS")) K = atoi(e) > 0 ? atoi(e) : K;
-  if (K > s_max) K = s_max;
-  int W = s_max / K;
+  const size_t xch = G == 2 ? (size_t)6 * ROW * sizeof(float) : 0;  // per consumer group
+  const size_t budget = kSmemBudget - 256;
+  // W consumer groups (G warps each) x K private stages per group.  Warps first (the kernel
+  // is latency-bound per warp), then deeper prefetch with whatever shared memory is left.
+  int W = (int)(budget / (stage + 16 + xch));
   if (W > 15) W = 15;
   if (const char* e = getenv("ROBSEG_LOSS_WARPS")) W = atoi(e) > 0 && atoi(e) <= W ? atoi(e) : W;
+  ROBSEG_REQUIRE(W >= 1, "C=%d: one stage does not fit in shared memory", p.C);
+  int K = (int)((budget - W * xch) / (W * (stage + 16)));
+  if (K > 4) K = 4;
+  if (const char* e = getenv("ROBSEG_LOSS_SLOTS")) K = atoi(e) > 0 && atoi(e) <= K ? atoi(e) : K;
   const int S = W * K;
   p.n_slots = K, p.n_consumers = W;
-  const size_t smem = S * stage + 2 * S * sizeof(uint64_t) + 128;
+  const size_t smem = S * stage + 2 * S * sizeof(uint64_t) + W * xch + 128;
 
   CUtensorMap tmap;
   const cuuint64_t dims[3] = {(cuuint64_t)p.HW, (cuuint64_t)p.C, (cuuint64_t)p.B};
@@ -535,15 +669,33 @@ static int launch_tma(const LossParams& p0, cudaStream_t stream) {
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ROBSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
 
-  auto kern = loss_tma_kernel<T, VEC>;
+  auto kern = loss_tma_kernel<T, VEC, G>;
   ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   const int max_useful = (p.num_tiles + W - 1) / W;
   if (grid > max_useful) grid = max_useful;
   if (grid < 1) grid = 1;
-  kern<<<grid, 32 * (W + 1), smem, stream>>>(tmap, p);
+  kern<<<grid, 32 * (W * G + 1), smem, stream>>>(tmap, p);
   ROBSEG_LAUNCH_CHECK();
   return 0;
+}
+
+// G = 2 (two warps split the channel axis of one stage) when a stage is so large that fewer
+// than 15 one-warp groups fit; only for per-lane vectors <= 8 bytes (register budget of a
+// 1024-thread block).
+template <typename T, int VEC>
+static int launch_tma_pick(const LossParams& p, cudaStream_t stream) {
+  const size_t stage = (size_t)p.C * 32 * VEC * sizeof(T);
+  // Measured: splitting the channel axis between two warps does not beat one warp per stage
+  // once the loads compile to LDS (the kernel is then bound by the memory system, not by
+  // warp-level parallelism); kept selectable for experiments and covered by the tests.
+  (void)stage;
+  bool pair = false;
+  if (const char* e = getenv("ROBSEG_LOSS_G")) pair = atoi(e) == 2;
+  if constexpr (VEC * sizeof(T) <= 4) {
+    if (pair) return launch_tma<T, VEC, 2>(p, stream);
+  }
+  return launch_tma<T, VEC, 1>(p, stream);
 }
 
 template <typename T>
@@ -616,12 +768,13 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
     const int vec = pick_vec(C, esize);
     tiles_per_img = (int)((HW + 32 * vec - 1) / (32 * vec));
     if (dtype == ROBSEG_F32) {
-      rc = vec == 4 ? launch_tma<float, 4>(p, stream)
-                    : vec == 2 ? launch_tma<float, 2>(p, stream) : launch_tma<float, 1>(p, stream);
+      rc = vec == 4 ? launch_tma_pick<float, 4>(p, stream)
+                    : vec == 2 ? launch_tma_pick<float, 2>(p, stream)
+                               : launch_tma_pick<float, 1>(p, stream);
     } else {
-      rc = vec == 8 ? launch_tma<__nv_bfloat16, 8>(p, stream)
-                    : vec == 4 ? launch_tma<__nv_bfloat16, 4>(p, stream)
-                               : launch_tma<__nv_bfloat16, 2>(p, stream);
+      rc = vec == 8 ? launch_tma_pick<__nv_bfloat16, 8>(p, stream)
+                    : vec == 4 ? launch_tma_pick<__nv_bfloat16, 4>(p, stream)
+                               : launch_tma_pick<__nv_bfloat16, 2>(p, stream);
     }
   } else {
     tiles_per_img = (int)((HW + 31) / 32);

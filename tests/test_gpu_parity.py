@@ -114,6 +114,26 @@ def test_loss_kernel_bf16(mods, shape, kind):
     np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("env", [{"ROBSEG_LOSS_G": "2"}, {"ROBSEG_LOSS_VEC": "1", "ROBSEG_LOSS_SLOTS": "2", "ROBSEG_LOSS_WARPS": "3"},
+                                 {"ROBSEG_LOSS_G": "2", "ROBSEG_LOSS_VEC": "1"}])
+def test_loss_kernel_alternative_schedules(mods, env, monkeypatch):
+    """The experiment knobs (two warps per stage, narrower rows, deeper per-warp rings) must not
+    change results: same outputs as the default schedule, bit for bit, incl. ring wrap-around."""
+    B, C, H, W = 2, 150, 96, 128
+    z, y, w = make_problem(B, C, H, W, seed=11)
+    z, y, w = z.to(dev()), y.to(dev()), w.to(dev())
+    for kind in ("mask-ce-bal", "js-avg", "argmax"):
+        ref = mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_grad=kind != "argmax")
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            out = mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_grad=kind != "argmax")
+        assert torch.equal(out.pred, ref.pred) and torch.equal(out.correct, ref.correct)
+        if kind != "argmax":
+            assert rel(out.dlogits.cpu().numpy(), ref.dlogits.cpu().numpy()) <= 2e-6
+            assert torch.allclose(out.loss_img, ref.loss_img, rtol=1e-6)
+
+
 def test_loss_kernel_edge_cases(mods):
     o = mods.ops
     # all pixels ignored; all pixels wrong (mask empty); all correct; saturated logits (JS finite)
