@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-upsample", action="store_true",
+                    help="keep F.interpolate for the consumer's final logit up-sampling (default: robseg kernels)")
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
     return ap.parse_args()
 
@@ -175,7 +177,8 @@ def run_ours(args):
         return run_micro(args, mods, dev, rank, world)
 
     torch.manual_seed(0)
-    model = mods["consumers"].upernet_convnext(args.variant, args.classes).to(dev).eval()
+    model = mods["consumers"].upernet_convnext(args.variant, args.classes,
+                                               fast_upsample=not args.stock_upsample).to(dev).eval()
     for p in model.parameters():
         p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
     B, C, S = args.batch, args.classes, args.size
@@ -257,6 +260,8 @@ def run_ours(args):
             "image_iterations_per_step": iters_per_step * world,
             "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + 1), "model_bwd_per_step": len(LOSSES) * args.n_iter,
             "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)",
+            "final_logit_upsample": "F.interpolate (stock)" if args.stock_upsample else
+            "robseg_upsample_bilinear_fwd/_bwd (SURVEY 8f-1; --stock-upsample restores F.interpolate)",
             "l2_note": "inputs larger than L2: logits/dlogits 2x%.2f GB per launch" % (B * C * S * S * 4 / 1e9),
             "parallelism": f"image-sharded dp{world}, one int64 all-reduce per step",
             "epilogue": "evalSEA greedy worst-case mIoU once per run outside the steps: %.1f ms (mIoU %.4f)" % (t_ep, miou),
@@ -268,7 +273,7 @@ def run_ours(args):
         "e2e": {"value": round(value_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,1> (fused loss+dlogits, C=%d)" % C,
+        "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
                      "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s",
                      "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C),
                      "peak_source": peaks[1], "launches_timed": lg[2],
@@ -345,8 +350,29 @@ def run_micro(args, mods, dev, rank, world):
             z.numel() * es + 16 * y.numel())
     time_it("apgd_step", lambda: ops.apgd_step(x, xa, xo, gr, step, 8 / 255, 0.75, xn), 20 * x.numel())
     pred = z.argmax(1)
-    time_it("pixel_hist/counts", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel())
-    time_it("pixel_hist/full", lambda: ops.pixel_hist(pred, y, C, want_hist=True, want_counts=False), 16 * y.numel())
+    time_it("pixel_hist/counts uniform-random", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel())
+    time_it("pixel_hist/full uniform-random", lambda: ops.pixel_hist(pred, y, C, want_hist=True, want_counts=False), 16 * y.numel())
+    ys = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.8, torch.full_like(y, 3), y)  # 80 % one class
+    ps = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.7, ys, pred)
+    time_it("pixel_hist/counts skewed-80pct", lambda: ops.pixel_hist(ps, ys, C), 16 * y.numel())
+    blk = torch.randint(0, C, (B, S // 32, S // 32), device=dev, generator=g)  # 32x32 constant regions
+    yc = blk.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
+    pc = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.9, yc, pred)
+    time_it("pixel_hist/counts coherent-32x32", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel())
+    if args.micro_dtype == "fp32":
+        import torch.nn.functional as F
+
+        Bu = min(B, 16)
+        low = torch.randn(Bu, C, S // 4, S // 4, device=dev, generator=g)
+        gup = torch.randn(Bu, C, S, S, device=dev, generator=g)
+        nb = 4 * (low.numel() + gup.numel())
+        time_it("upsample_fwd x4 (ours)", lambda: ops._upsample_fwd(low, S, S), nb)
+        time_it("upsample_bwd x4 (ours)", lambda: ops._upsample_bwd(gup, S // 4, S // 4), nb)
+        time_it("upsample_fwd x4 (ATen)", lambda: F.interpolate(low, size=(S, S), mode="bilinear", align_corners=False), nb)
+        lr = low.clone().requires_grad_()
+        up = F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False)
+        time_it("upsample_bwd x4 (ATen)", lambda: torch.autograd.grad(up, [lr], grad_outputs=gup, retain_graph=True), nb)
+        del up, lr, low, gup
     # the stock ATen chain of the reference on the same device (SURVEY 8d "also report")
     if args.micro_dtype == "fp32" and B <= 16:
         import torch.nn.functional as F
@@ -454,6 +480,12 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
+    # all the host threads the process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+    try:
+        n_thr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_thr = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_thr))
     for i in range(args.warmup):
         _cpu_sample(args, LOSSES[i % 3], 50 + i)
     t, n, kind = 0.0, 0, None

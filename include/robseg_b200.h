@@ -188,6 +188,20 @@ int robseg_pixel_hist(const int64_t* pred, const int64_t* labels, int n_img, int
 int robseg_sea_worst_acc(const int64_t* inter, const int64_t* tgt, int A, int N, int C,
                          float* acc_an, float* worst_n, robseg_stream_t stream);
 
+/*
+ * Bilinear up-sampling, align_corners=False, of [planes, h, w] fp32 to [planes, H, W] and its
+ * adjoint (planes = B*C).  Replaces the consumer's final logit up-sampling
+ * nn.functional.interpolate(logits, size=input.shape[2:], mode="bilinear", align_corners=False)
+ * (semseg/models/uperforseg.py:416-418, semseg/models/segmenter.py:228) and its autograd
+ * backward -- SURVEY.md section 8f rank 1.  Index/weight arithmetic as ATen's
+ * area_pixel_compute_source_index.  The backward is a deterministic gather (no atomics):
+ * gin[p,y,x] = sum over the output pixels whose taps include (y,x) of weight * gout.
+ */
+int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int h, int w, float* out, int H,
+                                 int W, robseg_stream_t stream);
+int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W, float* gin, int h,
+                                 int w, robseg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

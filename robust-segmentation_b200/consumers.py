@@ -95,15 +95,25 @@ class UperHead(nn.Module):
 
 
 class UperNetConvNeXt(nn.Module):
-    def __init__(self, variant="T", n_cls=150):
+    """``fast_upsample=True`` routes the final logit up-sampling (the only [B,C,H,W]-sized op of
+    the model) through robseg's kernels instead of ``F.interpolate``."""
+
+    def __init__(self, variant="T", n_cls=150, fast_upsample=False):
         super().__init__()
+        self.fast_upsample = fast_upsample
         self.backbone = ConvNeXtCvSt(CONVNEXT[variant])
         self.decode_head = UperHead(n_cls)
         self.aux_head = nn.Sequential(conv_bn_relu(WIDTHS[2], 256, 3), nn.Conv2d(256, n_cls, 1))
 
     def forward(self, x, lbl=None):
         feats = self.backbone(x)
-        logits = F.interpolate(self.decode_head(feats), size=x.shape[2:], mode="bilinear", align_corners=False)
+        low = self.decode_head(feats)
+        if self.fast_upsample and low.is_cuda and low.dtype == torch.float32:
+            from . import ops
+
+            logits = ops.upsample_bilinear(low, x.shape[2:])
+        else:
+            logits = F.interpolate(low, size=x.shape[2:], mode="bilinear", align_corners=False)
         if lbl is None:
             return logits
         aux = F.interpolate(self.aux_head(feats[2]), size=x.shape[2:], mode="bilinear", align_corners=False)
@@ -111,8 +121,8 @@ class UperNetConvNeXt(nn.Module):
         return (loss, logits) if self.training else logits
 
 
-def upernet_convnext(variant="T", n_cls=150):
-    return UperNetConvNeXt(variant, n_cls)
+def upernet_convnext(variant="T", n_cls=150, fast_upsample=False):
+    return UperNetConvNeXt(variant, n_cls, fast_upsample)
 
 
 class TinySegNet(nn.Module):

@@ -1,0 +1,380 @@
+// Bilinear up-sampling (align_corners=False) of the consumer's low-resolution logits to the
+// input size, forward and backward: SURVEY.md section 8f rank 1, the caller-side neighbour of
+// the loss kernel (semseg/models/uperforseg.py:416-418, semseg/models/segmenter.py:228).
+//
+// The stock ATen pair costs ~19 % of the GPU time of a SEA step on B200 (profiles/
+// r01_launches_bench.md): the forward runs far below write bandwidth and the backward scatters
+// with float atomics.  Here the forward is a pure streaming write (each thread produces four
+// adjacent outputs, the 16x smaller input stays in L1/L2) and the backward is a deterministic
+// GATHER: a CTA stages the output-gradient region that touches its tile of input cells in
+// shared memory (coalesced, each element read once from HBM), reduces along x, then along y.
+// No atomics, bit-reproducible.  Index and weight arithmetic follows ATen's
+// area_pixel_compute_source_index: src = scale*(dst+0.5)-0.5 clamped at 0, i0 = floor(src),
+// i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1.
+#include "common.cuh"
+
+namespace robseg {
+
+struct Tap {
+  int i0, i1;
+  float w0, w1;
+};
+
+__device__ __forceinline__ Tap make_tap(int dst, float scale, int in_size) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  Tap t;
+  t.i0 = min((int)src, in_size - 1);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.w1 = src - (float)t.i0;
+  t.w0 = 1.f - t.w1;
+  return t;
+}
+
+// out[p, Y, X..X+3]; grid (ceil(W/4/128), H, plane groups), block 128.  The taps depend only on
+// (Y, X), so a block computes them once and then streams over its planes.  For up-sampling
+// ratios >= 2 the four outputs of a thread read at most three adjacent input columns: 6 loads
+// per 16-byte store instead of 16.
+__global__ void __launch_bounds__(128)
+    upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h,
+                        int w, int H, int W, float sy, float sx) {
+  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int Y = blockIdx.y;
+  if (X0 >= W) return;
+  const Tap ty = make_tap(Y, sy, h);
+  Tap tx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tx[j] = make_tap(min(X0 + j, W - 1), sx, w);
+  const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const int cbase = tx[0].i0;
+  const bool narrow = tx[3].i1 - cbase <= 2;
+  const int c1 = min(cbase + 1, w - 1), c2 = min(cbase + 2, w - 1);
+  int o0[4], o1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o0[j] = tx[j].i0 - cbase, o1[j] = tx[j].i1 - cbase;
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* r0 = in + (p * h + ty.i0) * w;
+    const float* r1 = in + (p * h + ty.i1) * w;
+    float v[4];
+    if (narrow) {
+      const float a0 = __ldg(r0 + cbase), a1 = __ldg(r0 + c1), a2 = __ldg(r0 + c2);
+      const float b0 = __ldg(r1 + cbase), b1 = __ldg(r1 + c1), b2 = __ldg(r1 + c2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = o0[j] == 0 ? a0 : (o0[j] == 1 ? a1 : a2);
+        const float b = o1[j] == 0 ? a0 : (o1[j] == 1 ? a1 : a2);
+        const float c = o0[j] == 0 ? b0 : (o0[j] == 1 ? b1 : b2);
+        const float d = o1[j] == 0 ? b0 : (o1[j] == 1 ? b1 : b2);
+        v[j] = ty.w0 * (tx[j].w0 * a + tx[j].w1 * b) + ty.w1 * (tx[j].w0 * c + tx[j].w1 * d);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = __ldg(r0 + tx[j].i0), b = __ldg(r0 + tx[j].i1);
+        const float c = __ldg(r1 + tx[j].i0), d = __ldg(r1 + tx[j].i1);
+        v[j] = ty.w0 * (tx[j].w0 * a + tx[j].w1 * b) + ty.w1 * (tx[j].w0 * c + tx[j].w1 * d);
+      }
+    }
+    float* o = out + (p * H + Y) * W + X0;
+    if (vec) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (X0 + j < W) o[j] = v[j];
+    }
+  }
+}
+
+// Deterministic gather backward.  Block = 256 threads, tile TY x TX input cells; the block
+// builds the per-cell tap tables once (they depend only on the cell), then loops over its
+// planes: stage the output-gradient region in shared memory (each element read once, coalesced),
+// reduce along x, reduce along y, write each input cell exactly once.
+// Shared layout: region [RY][RXP] | xred [TX][RYP] | wx [TX][KX] | wy [TY][KY] | xs [TX] | ys [TY]
+__global__ void __launch_bounds__(256)
+    upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
+                        int w, int H, int W, float sy, float sx, int TY, int TX, int RY, int RX, int KY,
+                        int KX) {
+  extern __shared__ float shm[];
+  const int RXP = RX | 1, RYP = RY | 1;  // odd strides: conflict-free column walks
+  float* region = shm;
+  float* xred = region + (size_t)RY * RXP;
+  float* wx = xred + (size_t)TX * RYP;
+  float* wy = wx + (size_t)TX * KX;
+  int* xs = reinterpret_cast<int*>(wy + (size_t)TY * KY);
+  int* ys = xs + TX;
+  const int cy0 = blockIdx.y * TY, cx0 = blockIdx.x * TX;
+  const float inv_sy = 1.f / sy, inv_sx = 1.f / sx;
+  // first output row/col whose taps can touch the tile: i1 >= c0  <=>  src > c0 - 1
+  int Y0 = (int)floorf(((float)cy0 - 1.f + 0.5f) * inv_sy - 0.5f) - 1;
+  int X0 = (int)floorf(((float)cx0 - 1.f + 0.5f) * inv_sx - 0.5f) - 1;
+  Y0 = max(Y0, 0), X0 = max(X0, 0);
+  X0 &= ~3;  // keep rows 16-byte aligned for the vector loads
+  // ---- tap tables (once per block) ---------------------------------------------------------------
+  for (int i = threadIdx.x; i < TX + TY; i += blockDim.x) {
+    const bool isx = i < TX;
+    const int c = isx ? cx0 + i : cy0 + (i - TX);
+    const int in_size = isx ? w : h, out_size = isx ? W : H, K = isx ? KX : KY;
+    const float inv_s = isx ? inv_sx : inv_sy, sc = isx ? sx : sy;
+    float* wt = isx ? wx + (size_t)i * KX : wy + (size_t)(i - TX) * KY;
+    int a = (int)floorf(((float)c - 1.f + 0.5f) * inv_s - 0.5f) - 1;
+    a = max(a, isx ? X0 : Y0);
+    for (int k = 0; k < K; ++k) {
+      const int o = a + k;
+      float wgt = 0.f;
+      if (c < in_size && o < out_size) {
+        const Tap t = make_tap(o, sc, in_size);
+        wgt = (t.i0 == c ? t.w0 : 0.f) + (t.i1 == c ? t.w1 : 0.f);
+      }
+      wt[k] = wgt;
+    }
+    (isx ? xs[i] : ys[i - TX]) = a - (isx ? X0 : Y0);
+  }
+  const bool vec = (W % 4 == 0) && (RX % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) % 16 == 0);
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    __syncthreads();  // tables ready / previous plane's xred consumed
+    const float* src = gout + p * (int64_t)H * W;
+    // ---- stage the region (zero beyond the image) --------------------------------------------
+    if (vec) {
+      const int nx4 = RX / 4;
+      for (int i = threadIdx.x; i < RY * nx4; i += blockDim.x) {
+        const int r = i / nx4, c4 = i - r * nx4;
+        const int Y = Y0 + r, X = X0 + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (Y < H && X < W) v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)Y * W + X));
+        float* d = region + r * RXP + 4 * c4;
+        d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < RY * RX; i += blockDim.x) {
+        const int r = i / RX, c = i - r * RX;
+        const int Y = Y0 + r, X = X0 + c;
+        region[r * RXP + c] = (Y < H && X < W) ? __ldcs(src + (int64_t)Y * W + X) : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- reduce along x: lanes walk rows (odd stride), one cell column per group of RY threads -
+    for (int i = threadIdx.x; i < RY * TX; i += blockDim.x) {
+      const int cx = i / RY, r = i - cx * RY;
+      const float* row = region + r * RXP + xs[cx];
+      const float* wt = wx + (size_t)cx * KX;
+      float acc = 0.f;
+      for (int k = 0; k < KX; ++k) acc = fmaf(wt[k], row[k], acc);
+      xred[cx * RYP + r] = acc;
+    }
+    __syncthreads();
+    // ---- reduce along y and write each input cell once -------------------------------------------
+    for (int i = threadIdx.x; i < TY * TX; i += blockDim.x) {
+      const int cy = i / TX, cx = i - cy * TX;
+      const int celly = cy0 + cy, cellx = cx0 + cx;
+      if (celly >= h || cellx >= w) continue;
+      const float* col = xred + cx * RYP + ys[cy];
+      const float* wt = wy + (size_t)cy * KY;
+      float acc = 0.f;
+      for (int k = 0; k < KY; ++k) acc = fmaf(wt[k], col[k], acc);
+      gin[(p * h + celly) * (int64_t)w + cellx] = acc;
+    }
+  }
+}
+
+// ---- exact x4 specialisations (H == 4h, W == 4w: UperNet's logits) ----------------------------
+// Output block (4 rows x 4 cols) <-> input cell (a, b): its taps only touch cells a-1..a+1 x
+// b-1..b+1.  Dense 3-tap weight rows (zeros included, image borders folded in through
+// make_tap) make both directions branch-free.
+struct W3 {
+  float k[4][3];  // k[j][c]: weight of input (base-1+c) for output 4*base+j
+};
+
+__device__ __forceinline__ W3 make_w3(int base, float scale, int in_size) {
+  W3 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const Tap t = make_tap(4 * base + j, scale, in_size);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cell = base - 1 + c;
+      r.k[j][c] = (t.i0 == cell ? t.w0 : 0.f) + (t.i1 == cell ? t.w1 : 0.f);
+    }
+  }
+  return r;
+}
+
+// grid (ceil(w/128), h, plane groups), block 128: thread = one input cell column b of cell row a,
+// produces the 4x4 output block from 9 loads (separable: 3 rows x 4 horizontal outputs, then
+// vertical), stores four coalesced float4 rows.
+__global__ void __launch_bounds__(128)
+    upsample_fwd_x4_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h,
+                           int w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  if (b >= w) return;
+  const int H = 4 * h, W = 4 * w;
+  const W3 kx = make_w3(b, 0.25f, w), ky = make_w3(a, 0.25f, h);
+  const int cm = max(b - 1, 0), cp = min(b + 1, w - 1);
+  const int rm = max(a - 1, 0), rp = min(a + 1, h - 1);
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* base = in + p * (int64_t)h * w;
+    float hx[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float* row = base + (int64_t)(r == 0 ? rm : (r == 1 ? a : rp)) * w;
+      const float v0 = __ldg(row + cm), v1 = __ldg(row + b), v2 = __ldg(row + cp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hx[r][j] = kx.k[j][0] * v0 + kx.k[j][1] * v1 + kx.k[j][2] * v2;
+    }
+    float* o = out + (p * H + 4 * a) * (int64_t)W + 4 * b;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v;
+      v.x = ky.k[i][0] * hx[0][0] + ky.k[i][1] * hx[1][0] + ky.k[i][2] * hx[2][0];
+      v.y = ky.k[i][0] * hx[0][1] + ky.k[i][1] * hx[1][1] + ky.k[i][2] * hx[2][1];
+      v.z = ky.k[i][0] * hx[0][2] + ky.k[i][1] * hx[1][2] + ky.k[i][2] * hx[2][2];
+      v.w = ky.k[i][0] * hx[0][3] + ky.k[i][1] * hx[1][3] + ky.k[i][2] * hx[2][3];
+      __stcs(reinterpret_cast<float4*>(o + (int64_t)i * W), v);
+    }
+  }
+}
+
+// grid (ceil(w/32/warps), strips, plane groups), block 128 (4 warps side by side).  A lane owns
+// input cell column b and walks down the output rows of its strip of cell rows [a0, a1): one
+// coalesced float4 per output row straight from global memory, x-reduction in registers with
+// two shuffles (partials for the neighbouring cells), y-reduction in three rotating
+// accumulators; each input cell is written once.  No shared memory, no atomics.
+__global__ void __launch_bounds__(128)
+    upsample_bwd_x4_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
+                           int w, int strip) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
+  const int W = 4 * w, H = 4 * h;
+  const bool live = b < w;
+  const int bc = min(b, w - 1);
+  // transposed taps: weight of output 4*cell+j on input cell (cell-1+c)
+  const W3 kx = make_w3(bc, 0.25f, w);
+  const bool need_left = live && lane == 0 && b > 0;          // left neighbour lives in another warp
+  const bool need_right = live && (lane == 31 || b == w - 1) && b + 1 < w;
+  W3 kxl = kx, kxr = kx;
+  if (need_left) kxl = make_w3(b - 1, 0.25f, w);
+  if (need_right) kxr = make_w3(b + 1, 0.25f, w);
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* src = gout + p * (int64_t)H * W;
+    float acc_prev = 0.f, acc_cur = 0.f, acc_next = 0.f;  // cells a-1, a, a+1 of the current block row
+    for (int a = max(a0 - 1, 0); a <= min(a1, h - 1); ++a) {
+      const W3 ky = make_w3(a, 0.25f, h);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* row = src + (int64_t)(4 * a + i) * W;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) v = __ldcs(reinterpret_cast<const float4*>(row + 4 * b));
+        // partial sums of this float4 for cells b-1, b, b+1
+        float pl = kx.k[0][0] * v.x + kx.k[1][0] * v.y + kx.k[2][0] * v.z + kx.k[3][0] * v.w;
+        const float pc = kx.k[0][1] * v.x + kx.k[1][1] * v.y + kx.k[2][1] * v.z + kx.k[3][1] * v.w;
+        float pr = kx.k[0][2] * v.x + kx.k[1][2] * v.y + kx.k[2][2] * v.z + kx.k[3][2] * v.w;
+        float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's contribution to my cell
+        float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's contribution to my cell
+        if (lane == 0) from_left = 0.f;
+        if (lane == 31) from_right = 0.f;
+        if (need_left) {
+          const float4 u = __ldcs(reinterpret_cast<const float4*>(row + 4 * (b - 1)));
+          from_left = kxl.k[0][2] * u.x + kxl.k[1][2] * u.y + kxl.k[2][2] * u.z + kxl.k[3][2] * u.w;
+        }
+        if (need_right) {
+          const float4 u = __ldcs(reinterpret_cast<const float4*>(row + 4 * (b + 1)));
+          from_right = kxr.k[0][0] * u.x + kxr.k[1][0] * u.y + kxr.k[2][0] * u.z + kxr.k[3][0] * u.w;
+        } else if (b == w - 1) {
+          from_right = 0.f;
+        }
+        const float xr = (from_left + pc) + from_right;
+        acc_prev = fmaf(ky.k[i][0], xr, acc_prev);
+        acc_cur = fmaf(ky.k[i][1], xr, acc_cur);
+        acc_next = fmaf(ky.k[i][2], xr, acc_next);
+        (void)pl, (void)pr;
+      }
+      // cell row a-1 has now received everything (block rows a-2 .. a)
+      if (live && a - 1 >= a0 && a - 1 < a1) gin[(p * h + (a - 1)) * (int64_t)w + b] = acc_prev;
+      acc_prev = acc_cur, acc_cur = acc_next, acc_next = 0.f;
+    }
+    // the last cell row of the strip when the strip ends at the image border
+    if (live && a1 == h && h - 1 >= a0) gin[(p * h + (h - 1)) * (int64_t)w + b] = acc_prev;
+  }
+}
+
+}  // namespace robseg
+
+using namespace robseg;
+
+extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int h, int w, float* out,
+                                            int H, int W, robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(in && out, "NULL pointer");
+  ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0 && H <= 65535, "bad shape");
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  if (H == 4 * h && W == 4 * w && reinterpret_cast<uintptr_t>(out) % 16 == 0 && h <= 65535) {
+    const int gx4 = (w + 127) / 128;
+    int64_t gz4 = ((int64_t)sm_count() * 32 + (int64_t)gx4 * h - 1) / ((int64_t)gx4 * h);
+    gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
+    if (gz4 > 65535) gz4 = 65535;
+    upsample_fwd_x4_kernel<<<dim3(gx4, h, (unsigned)gz4), 128, 0, stream>>>(in, out, planes, h, w);
+    ROBSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  const int gx = (W + 4 * 128 - 1) / (4 * 128);
+  // ~32 resident blocks per SM worth of (x, y) tiles; the rest of the parallelism is planes
+  int64_t gz = ((int64_t)sm_count() * 32 + (int64_t)gx * H - 1) / ((int64_t)gx * H);
+  if (gz < 1) gz = 1;
+  if (gz > planes) gz = planes;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)gx, (unsigned)H, (unsigned)gz);
+  upsample_fwd_kernel<<<grid, 128, 0, stream>>>(in, out, planes, h, w, H, W, sy, sx);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W, float* gin,
+                                            int h, int w, robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(gout && gin, "NULL pointer");
+  ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  if (H == 4 * h && W == 4 * w && reinterpret_cast<uintptr_t>(gout) % 16 == 0) {
+    const int gx4 = (w + 127) / 128;
+    int strip = 32;  // cell rows per thread strip: 2 halo block rows per strip (6 % extra reads)
+    if (strip > h) strip = h;
+    const int gy4 = (h + strip - 1) / strip;
+    int64_t gz4 = ((int64_t)sm_count() * 32 + (int64_t)gx4 * gy4 - 1) / ((int64_t)gx4 * gy4);
+    gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
+    if (gz4 > 65535) gz4 = 65535;
+    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 128, 0, stream>>>(gout, gin, planes, h, w,
+                                                                             strip);
+    ROBSEG_LAUNCH_CHECK();
+    return 0;
+  }
+  // tile of input cells per CTA: shrink until the staged output region fits ~48 KB
+  int TY = 8, TX = 32;
+  if (TX > w) TX = w;
+  if (TY > h) TY = h;
+  int RY, RX, KY, KX;
+  size_t smem;
+  for (;;) {
+    KY = (int)ceilf(2.f / sy) + 4, KX = (int)ceilf(2.f / sx) + 4;
+    RY = (int)ceilf((TY + 2) / sy) + 4 + KY;
+    RX = (((int)ceilf((TX + 2) / sx) + 8 + KX + 3) / 4) * 4;
+    smem = ((size_t)RY * (RX | 1) + (size_t)TX * (RY | 1) + (size_t)TX * KX + (size_t)TY * KY + TX + TY) *
+           sizeof(float);
+    if (smem <= 48 * 1024 || (TY == 1 && TX == 1)) break;
+    if (TX > 1 && (TX >= TY * 4 || TY == 1)) TX = (TX + 1) / 2; else TY = (TY + 1) / 2;
+  }
+  ROBSEG_REQUIRE(smem <= 200 * 1024, "up-sampling ratio too large (%dx%d -> %dx%d)", h, w, H, W);
+  ROBSEG_CUDA(cudaFuncSetAttribute(upsample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  const int gx = (w + TX - 1) / TX, gy = (h + TY - 1) / TY;
+  int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
+  if (gz < 1) gz = 1;
+  if (gz > planes) gz = planes;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+  upsample_bwd_kernel<<<grid, 256, smem, stream>>>(gout, gin, planes, h, w, H, W, sy, sx, TY, TX, RY, RX,
+                                                   KY, KX);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}

@@ -35,3 +35,28 @@ def install(reference_root=None):
         for n in names:
             setattr(m, n, getattr(src, n))
     return attacker
+
+
+def fast_logit_upsample(model):
+    """Route the final logit up-sampling of a reference model through robseg's kernels.
+
+    Works for models shaped like the reference's ``UperNetForSemanticSegmentation``
+    (semseg/models/uperforseg.py:382-439: ``backbone`` -> ``decode_head`` -> bilinear
+    up-sampling to the input size).  Only the eval-mode forward the attack uses is replaced;
+    the training forward (loss + aux head) is left alone."""
+    import types
+
+    from . import ops
+
+    if not (hasattr(model, "backbone") and hasattr(model, "decode_head")):
+        raise TypeError("fast_logit_upsample expects a model with .backbone and .decode_head")
+    stock_forward = model.forward
+
+    def forward(self, input=None, lbl=None):
+        if lbl is not None or self.training or not input.is_cuda:
+            return stock_forward(input, lbl)
+        low = self.decode_head(self.backbone(input))
+        return ops.upsample_bilinear(low.float(), input.shape[2:])
+
+    model.forward = types.MethodType(forward, model)
+    return model

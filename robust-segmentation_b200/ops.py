@@ -297,6 +297,55 @@ def sea_worst_acc(inter, tgt):
     return acc, worst
 
 
+def _upsample_fwd(x, H, W):
+    _need_cuda(x)
+    lib = _lib.load()
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise TypeError("upsample_bilinear expects a 4-D float32 CUDA tensor")
+    x = x.contiguous()
+    B, Cn, h, w = x.shape
+    out = torch.empty((B, Cn, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _timed("upsample_fwd", 4 * (x.numel() + out.numel())):
+        rc = lib.robseg_upsample_bilinear_fwd(x.data_ptr(), B * Cn, h, w, out.data_ptr(), H, W, _stream())
+    _lib.check(rc, "robseg_upsample_bilinear_fwd")
+    _lib.count(1)
+    return out
+
+
+def _upsample_bwd(g, h, w):
+    _need_cuda(g)
+    lib = _lib.load()
+    g = g.contiguous()
+    if g.dtype != torch.float32:
+        g = g.float()
+    B, Cn, H, W = g.shape
+    gin = torch.empty((B, Cn, h, w), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device), _timed("upsample_bwd", 4 * (g.numel() + gin.numel())):
+        rc = lib.robseg_upsample_bilinear_bwd(g.data_ptr(), B * Cn, H, W, gin.data_ptr(), h, w, _stream())
+    _lib.check(rc, "robseg_upsample_bilinear_bwd")
+    _lib.count(1)
+    return gin
+
+
+class _UpsampleBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        ctx.hw = (x.shape[2], x.shape[3])
+        return _upsample_fwd(x, H, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _upsample_bwd(g, *ctx.hw), None, None
+
+
+def upsample_bilinear(x, size):
+    """Drop-in for ``F.interpolate(x, size=size, mode="bilinear", align_corners=False)`` on fp32
+    NCHW CUDA tensors (robseg_upsample_bilinear_fwd / _bwd): streaming forward, deterministic
+    gather backward.  SURVEY.md section 8f rank 1."""
+    H, W = (size, size) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    return _UpsampleBilinear.apply(x, H, W)
+
+
 # ----------------------------------------------------------------------------------------------
 # torch.ops.robseg.* : the same kernels as dispatcher-visible custom ops.  ``pixel_loss`` carries
 # an autograd formula so the criterion_dict-compatible callables stay differentiable.

@@ -202,6 +202,8 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
         x_adv = ops.project_linf(None, x, eps, noise=t)
     if x_init is not None:
         x_adv = x_init.detach().float().contiguous().clone()
+    if verbose and logger is None:
+        logger = Logger(None)
     if logger is not None:  # attacker.py:302-305 (one host read per call, labels only)
         n_bg = int((y == ignore_index).sum())
         if n_bg > 0:
@@ -250,8 +252,6 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     done_host = torch.zeros([1], dtype=torch.int32).pin_memory() if early_stop else None
     copied = None
     checks = apgd_schedule(n_iter)
-    if verbose and logger is None:
-        logger = Logger(None)
 
     for i in range(n_iter):
         # ---- gradient step (attacker.py:388-410) ---------------------------------------------

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/gpus.txt
+(timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err)
+(timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err)
+cat gpurun_out/gpus.txt; head -c 3000 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err; head -c 1500 gpurun_out/bench_ref_n2.json; tail -3 gpurun_out/bench_ref_n2.err

@@ -416,6 +416,62 @@ def test_apgd_train_vs_oracle_same_device_model(mods, golden):
     assert (np.abs(xb.cpu().numpy() - g["x_best"]) > 1e-6).mean() <= 0.08
 
 
+def test_early_stop_freezes_state_exactly(mods, golden):
+    """All pixels mislabelled -> accuracy is 0 from the start -> the reference breaks after the
+    first iteration (attacker.py:568-569).  The drop-in notices one iteration late but the device
+    freezes the state, so the outputs equal an oracle run that stopped at the same iteration."""
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden("apgd_train40")
+    model = _tiny(mods, g)
+    cpu_model = _tiny(mods, g).cpu()
+    for m in (model, cpu_model):  # class 4 can never win the argmax; label every pixel with it
+        with torch.no_grad():
+            m.c2.bias[4] = -100.0
+    x = torch.from_numpy(g["x"])
+    y = torch.full(g["y"].shape, 4, dtype=torch.int64)
+    x0 = O.random_start(g["x"], float(g["eps"]), g["noise"])
+    rec = _Rec(model).eval()
+    xb, acc, lb, xba = mods.attacker.apgd_train(
+        rec, x.to(dev()), y.to(dev()), "Linf", float(g["eps"]), n_iter=12, use_rs=False, loss="ce-avg",
+        track_loss="ce-avg", early_stop=True, x_init=torch.from_numpy(x0).to(dev()), num_classes=int(g["C"]))
+    assert len(rec.inputs) <= 4  # initial point + at most three iterations, not 13
+    om = O.TorchModelAdapter(cpu_model)
+    oxb, oacc, olb, oxba = O.apgd_train(om, g["x"], y.numpy(), float(g["eps"]), n_iter=12, loss="ce-avg",
+                                        early_stop=True, x_init=x0)
+    assert float(acc.sum()) == 0.0 and float(oacc.sum()) == 0.0
+    assert (np.abs(xba.cpu().numpy() - oxba) > 1e-6).mean() <= 0.02
+    assert (np.abs(xb.cpu().numpy() - oxb) > 1e-6).mean() <= 0.02
+    np.testing.assert_allclose(lb.cpu().numpy(), olb, rtol=1e-4)
+
+
+def test_verbose_path_and_bf16_consumer(mods, capsys):
+    """verbose=True keeps the reference's per-iteration mAcc/aAcc/mIoU report (attacker.py:500-515);
+    a consumer that emits bf16 logits runs through the bf16 kernel."""
+    C = 7
+    model = mods.consumers.TinySegNet(C, seed=2).to(dev()).eval()
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 16, 16, generator=g).to(dev())
+    with torch.no_grad():
+        y = model(x).argmax(1)
+    y[0, :2] = -1
+    mods.attacker.apgd_train(model, x, y, "Linf", 8 / 255, n_iter=4, loss="mask-ce-avg", track_loss="ce-avg",
+                             verbose=True, num_classes=C)
+    out = capsys.readouterr().out
+    assert "iteration: 3" in out and "mIoU=" in out and "pixels are masked out" in out
+
+    class Bf16(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            return self.m(x).bfloat16()
+
+    xb, acc, lb, xba = mods.attacker.apgd_train(Bf16(model).eval(), x, y, "Linf", 8 / 255, n_iter=4,
+                                                loss="js-avg", track_loss="ce-avg", num_classes=C)
+    assert torch.isfinite(lb).all() and float((xba - x).abs().max()) <= 8 / 255 + 1e-6
+
+
 @pytest.mark.parametrize("tag,cls,los", [("pgd1_pgd", "Pgd_Attack_1", "pgd"), ("pgd_maskce", "Pgd_Attack", "mask-ce-avg"),
                                          ("pgd_js", "Pgd_Attack", "js-avg")])
 def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
@@ -442,6 +498,44 @@ def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
     atk2 = getattr(mods.val, cls)(epsilon=float(g["eps"]), num_iter=1, los=los, input_grad_only=True)
     atk2.adv_attack(model, x, y)
     assert all(p.grad is None for p in model.parameters())
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 8, 8, 32, 32), (1, 3, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32),
+                                   (2, 150, 32, 32, 128, 128), (1, 1, 6, 6, 6, 6), (1, 2, 9, 7, 5, 4)])
+def test_upsample_bilinear_vs_torch(mods, shape):
+    """robseg_upsample_bilinear_fwd/_bwd vs F.interpolate(..., 'bilinear', align_corners=False) and
+    its autograd backward; the backward is a gather, so repeated runs are bit-identical."""
+    B, C, h, w, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, C, h, w, generator=g).to(dev())
+    go = torch.randn(B, C, H, W, generator=g).to(dev())
+    xr = x.clone().requires_grad_()
+    ref = torch.nn.functional.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False)
+    (gref,) = torch.autograd.grad(ref, [xr], grad_outputs=go)
+    xo = x.clone().requires_grad_()
+    out = mods.ops.upsample_bilinear(xo, (H, W))
+    (gours,) = torch.autograd.grad(out, [xo], grad_outputs=go)
+    assert rel(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 2e-6
+    assert rel(gours.cpu().numpy(), gref.cpu().numpy()) <= 1e-5
+    out2 = mods.ops.upsample_bilinear(xo, (H, W))
+    (g2,) = torch.autograd.grad(out2, [xo], grad_outputs=go)
+    assert torch.equal(g2, gours) and torch.equal(out2, out)
+    # adjointness: <U x, g> == <x, U^T g>
+    lhs = float((out.detach().double() * go.double()).sum())
+    rhs = float((x.double() * gours.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_fast_upsample_consumer_matches_stock(mods):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    m = mods.consumers.upernet_convnext("T", 21).to(dev()).eval()
+    x = torch.rand(1, 3, 64, 64, device=dev())
+    with torch.no_grad():
+        a = m(x)
+        m.fast_upsample = True
+        b = m(x)
+    assert rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
 
 
 def test_custom_ops_registered(mods):
