@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reforward", action="store_true",
+                    help="re-forward every adversarial batch for its argmax map like tools/infer.py "
+                         "(default: the attack returns it, SURVEY 8f-2)")
     ap.add_argument("--stock-upsample", action="store_true",
                     help="keep F.interpolate for the consumer's final logit up-sampling (default: robseg kernels)")
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
@@ -129,12 +132,18 @@ def sea_step(mods, model, x, y, w, args, world, e2e_host=None):
     preds = []
     x_advs = []
     for loss in LOSSES:
-        x_adv, _, acc = att.apgd_largereps(
-            model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
-            track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C)
-        with torch.no_grad():
-            out = model(x_adv)
-        preds.append(ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred)
+        if args.reforward:  # the reference's flow: re-forward every adversarial batch (tools/infer.py:82-90)
+            x_adv, _, acc = att.apgd_largereps(
+                model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
+                track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C)
+            with torch.no_grad():
+                out = model(x_adv)
+            pred = ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred
+        else:  # the attack hands back the argmax map of its adversarial point
+            x_adv, _, acc, pred = att.apgd_largereps(
+                model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
+                track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C, return_pred=True)
+        preds.append(pred)
         x_advs.append(x_adv)
     cnt = ops.pixel_hist(torch.stack(preds).flatten(0, 1), y, C)
     inter, tgt, prd = (cnt[k].view(len(LOSSES), B, C) for k in ("inter", "tgt", "prd"))
@@ -258,7 +267,10 @@ def run_ours(args):
                         f"(3/3/4 @ 2eps/1.5eps/eps), UperNet-ConvNeXt-{args.variant}_CVST random init, "
                         f"{C} classes, {S}x{S}, batch {B} per GPU, eps {args.eps:g}/255",
             "image_iterations_per_step": iters_per_step * world,
-            "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + 1), "model_bwd_per_step": len(LOSSES) * args.n_iter,
+            "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + (1 if args.reforward else 0)),
+            "model_bwd_per_step": len(LOSSES) * args.n_iter,
+            "adversarial_argmax": "re-forward of x_adv (tools/infer.py:82-90)" if args.reforward else
+            "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)",
             "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)",
             "final_logit_upsample": "F.interpolate (stock)" if args.stock_upsample else
             "robseg_upsample_bilinear_fwd/_bwd (SURVEY 8f-1; --stock-upsample restores F.interpolate)",

@@ -169,8 +169,12 @@ def _track_values(out, loss_name, track_loss, logits, y, weights):
 
 def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbose=False,
                is_train=False, early_stop=False, track_loss=None, logger=None, y_target=None,
-               ignore_index=-1, x_init=None, num_classes=21, weights=None):
+               ignore_index=-1, x_init=None, num_classes=21, weights=None, return_pred=False):
     """APGD (L-inf) with the SEA losses; returns ``(x_best, acc, loss_best, x_best_adv)``.
+
+    ``return_pred=True`` (extension) appends ``pred_best``: the argmax map of
+    ``x_best_adv`` as seen during the attack, which lets the SEA driver skip the re-forward of
+    every adversarial batch (tools/infer.py:82-90).
 
     Mirrors semseg/attacker.py:260-571 step for step; see the module docstring for the
     kernel each block of the reference maps to."""
@@ -214,11 +218,13 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     if weights is not None and loss == "mask-ce-bal":
         w_dev = weights.to(device=device, dtype=torch.float32)  # hoisted H2D
 
+    keep_pred = verbose or return_pred
+
     def forward_backward(x_in_buf, need_grad, dbuf):
         x_in = x_in_buf.detach().requires_grad_(need_grad)
         with torch.set_grad_enabled(need_grad):
             logits = model(x_in)
-        out = ops.loss_fwd_bwd(logits, y, loss, w_dev, want_grad=need_grad, want_pred=verbose,
+        out = ops.loss_fwd_bwd(logits, y, loss, w_dev, want_grad=need_grad, want_pred=keep_pred,
                                dlogits_out=dbuf)
         g = None
         if need_grad:
@@ -246,7 +252,7 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     grad_best = grad.clone()
     x_old = x_adv.clone()
     x_new = torch.empty_like(x_adv)
-    pred_best = out.pred if verbose else None
+    pred_best = out.pred if keep_pred else None
     flags = torch.zeros([3, bs], dtype=torch.int32, device=device)
     done = torch.zeros([1], dtype=torch.int32, device=device)
     done_host = torch.zeros([1], dtype=torch.int32).pin_memory() if early_stop else None
@@ -272,7 +278,7 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
         jobs = [(x_best_adv, x_adv, flags[0], None),
                 (x_best, x_adv, flags[1], None),
                 (grad_best, grad, flags[1], None)]
-        if verbose:
+        if keep_pred:
             jobs.append((pred_best, out.pred, flags[0], None))
         if i in checks:  # restart the halved rows from their best point (:546-548)
             jobs += [(x_adv, x_best, flags[2], flags[1]), (grad, grad_best, flags[2], flags[1])]
@@ -296,15 +302,18 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
             copied = torch.cuda.Event()
             copied.record()
 
+    if return_pred:
+        return x_best, acc, loss_best, x_best_adv, pred_best
     return x_best, acc, loss_best, x_best_adv
 
 
 def apgd_largereps(model, x, y, weights, norm="Linf", eps=8.0 / 255.0, n_iter=10, loss="ce",
                    verbose=False, n_restarts=1, log_path=None, early_stop=False, eot_iter=0,
-                   track_loss=None, use_rs=False, ignore_index=-1, num_classes=21):
+                   track_loss=None, use_rs=False, ignore_index=-1, num_classes=21, return_pred=False):
     """SEA's 3-stage large-eps schedule (semseg/attacker.py:662-728): iterations
     ``[.3n, .3n, rest]`` at ``[2 eps, 1.5 eps, eps]``, each stage started from the projection of
-    the previous stage's lowest-accuracy point.  Returns ``(x_adv, loss_best, acc)``."""
+    the previous stage's lowest-accuracy point.  Returns ``(x_adv, loss_best, acc)``
+    (+ ``pred`` of ``x_adv`` with ``return_pred=True``)."""
     if norm != "Linf":
         raise NotImplementedError()
     logger = Logger(log_path)
@@ -315,15 +324,21 @@ def apgd_largereps(model, x, y, weights, norm="Linf", eps=8.0 / 255.0, n_iter=10
     acc = torch.ones([x.shape[0]], device=x.device)
     x = x.detach().float().contiguous()
     x_init = None
-    loss_best = None
-    for inner_it, inner_eps in zip(n_iters, epss):
+    loss_best = pred = None
+    last = len(n_iters) - 1
+    for stage, (inner_it, inner_eps) in enumerate(zip(n_iters, epss)):
         if x_init is not None:
             x_init = ops.project_linf(x_init, x, inner_eps)
-        _, acc, loss_best, x_init = apgd_train(
+        res = apgd_train(
             model, x, y, n_iter=inner_it, use_rs=use_rs, verbose=verbose, loss=loss,
             eps=inner_eps, norm=norm, logger=logger, early_stop=early_stop,
             track_loss=track_loss, y_target=None, ignore_index=ignore_index, x_init=x_init,
-            num_classes=num_classes, weights=weights)
+            num_classes=num_classes, weights=weights, return_pred=return_pred and stage == last)
+        _, acc, loss_best, x_init = res[:4]
+        if return_pred and stage == last:
+            pred = res[4]
+    if return_pred:
+        return x_init, loss_best, acc, pred
     return x_init, loss_best, acc
 
 

@@ -444,6 +444,31 @@ def test_early_stop_freezes_state_exactly(mods, golden):
     np.testing.assert_allclose(lb.cpu().numpy(), olb, rtol=1e-4)
 
 
+def test_return_pred_equals_reforward(mods):
+    """the argmax map tracked inside the attack == argmax(model(x_adv)) of a re-forward."""
+    torch.backends.cudnn.allow_tf32 = False
+    C = 9
+    model = mods.consumers.TinySegNet(C, seed=4).to(dev()).eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(3, 3, 32, 32, generator=g).to(dev())
+    with torch.no_grad():
+        y = model(x).argmax(1)
+    for loss in ("mask-ce-bal", "js-avg"):
+        torch.manual_seed(3)
+        x_adv, lb, acc, pred = mods.attacker.apgd_largereps(
+            model, x, y, None, eps=8 / 255, n_iter=12, loss=loss, track_loss="ce-avg", use_rs=True,
+            early_stop=True, num_classes=C, return_pred=True)
+        with torch.no_grad():
+            again = model(x_adv).argmax(1)
+        assert torch.equal(pred, again)
+        assert torch.equal(acc, (again == y).float().flatten(1).mean(1))
+        torch.manual_seed(3)
+        x_adv2, lb2, acc2 = mods.attacker.apgd_largereps(
+            model, x, y, None, eps=8 / 255, n_iter=12, loss=loss, track_loss="ce-avg", use_rs=True,
+            early_stop=True, num_classes=C)
+        assert torch.equal(x_adv2, x_adv) and torch.equal(acc2, acc) and torch.equal(lb2, lb)
+
+
 def test_verbose_path_and_bf16_consumer(mods, capsys):
     """verbose=True keeps the reference's per-iteration mAcc/aAcc/mIoU report (attacker.py:500-515);
     a consumer that emits bf16 logits runs through the bf16 kernel."""

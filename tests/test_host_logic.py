@@ -121,9 +121,11 @@ def test_signature_parity_with_reference_surface(mods):
     assert sig.parameters["eps"].default == 8.0 / 255.0 and sig.parameters["n_iter"].default == 10
     assert sig.parameters["loss"].default == "ce" and sig.parameters["num_classes"].default == 21
     sig = inspect.signature(a.apgd_train)
-    assert list(sig.parameters) == ["model", "x", "y", "norm", "eps", "n_iter", "use_rs", "loss", "verbose",
-                                    "is_train", "early_stop", "track_loss", "logger", "y_target",
-                                    "ignore_index", "x_init", "num_classes", "weights"]
+    # the reference's 18 parameters in order; extensions (return_pred) may only follow them
+    assert list(sig.parameters)[:18] == ["model", "x", "y", "norm", "eps", "n_iter", "use_rs", "loss", "verbose",
+                                         "is_train", "early_stop", "track_loss", "logger", "y_target",
+                                         "ignore_index", "x_init", "num_classes", "weights"]
+    assert all(sig.parameters[k].default is False for k in list(sig.parameters)[18:])
     assert set(a.criterion_dict) == {"ce", "ce-avg", "mask-ce-avg", "mask-ce-bal", "js-avg"}
     assert list(inspect.signature(a.compute_iou_acc).parameters) == [
         "pred", "target", "n_cls", "verbose", "ignore_index", "device"]
