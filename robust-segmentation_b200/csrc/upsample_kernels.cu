@@ -235,67 +235,64 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// grid (ceil(w/32/warps), strips, plane groups), block 128 (4 warps side by side).  A lane owns
-// input cell column b and walks down the output rows of its strip of cell rows [a0, a1): one
-// coalesced float4 per output row straight from global memory, x-reduction in registers with
-// two shuffles (partials for the neighbouring cells), y-reduction in three rotating
-// accumulators; each input cell is written once.  No shared memory, no atomics.
-__global__ void __launch_bounds__(128)
+// grid (x groups, strips, plane groups), block = up to 8 warps side by side.  A warp covers 30
+// owned input cell columns plus one halo lane on each side (lane 0 and lane 31 only feed their
+// neighbours), so the x-reduction needs no cross-warp traffic and no special cases.  A lane walks
+// down the output rows of its strip of cell rows [a0, a1): one coalesced float4 per output row
+// straight from global memory, x-reduction in registers with two shuffles, y-reduction in three
+// rotating accumulators; each input cell is written once.  No shared memory, no atomics.
+constexpr int kBwdOwned = 30;
+
+__global__ void __launch_bounds__(256)
     upsample_bwd_x4_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
                            int w, int strip) {
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = gw * kBwdOwned + lane - 1;  // lane 0 / 31: halo columns
+  if (gw * kBwdOwned >= w) return;          // whole warp past the image
   const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
   const int W = 4 * w, H = 4 * h;
-  const bool live = b < w;
-  const int bc = min(b, w - 1);
-  // transposed taps: weight of output 4*cell+j on input cell (cell-1+c)
-  const W3 kx = make_w3(bc, 0.25f, w);
-  const bool need_left = live && lane == 0 && b > 0;          // left neighbour lives in another warp
-  const bool need_right = live && (lane == 31 || b == w - 1) && b + 1 < w;
-  W3 kxl = kx, kxr = kx;
-  if (need_left) kxl = make_w3(b - 1, 0.25f, w);
-  if (need_right) kxr = make_w3(b + 1, 0.25f, w);
+  const bool loads = b >= 0 && b < w;
+  const bool owns = loads && lane >= 1 && lane <= kBwdOwned;
+  const W3 kx = make_w3(min(max(b, 0), w - 1), 0.25f, w);  // transposed taps of my float4
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
-    const float* src = gout + p * (int64_t)H * W;
+    const float* src = gout + p * (int64_t)H * W + 4 * (int64_t)max(b, 0);
     float acc_prev = 0.f, acc_cur = 0.f, acc_next = 0.f;  // cells a-1, a, a+1 of the current block row
-    for (int a = max(a0 - 1, 0); a <= min(a1, h - 1); ++a) {
+    const int a_first = max(a0 - 1, 0), a_last = min(a1, h - 1);
+    float4 v[4], nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (loads) nxt[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(4 * a_first + i) * W));
+    }
+    for (int a = a_first; a <= a_last; ++a) {
       const W3 ky = make_w3(a, 0.25f, h);
 #pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = nxt[i];
+      if (a < a_last) {  // prefetch the next block row while this one is reduced
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (loads) nxt[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(4 * (a + 1) + i) * W));
+      }
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float* row = src + (int64_t)(4 * a + i) * W;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) v = __ldcs(reinterpret_cast<const float4*>(row + 4 * b));
         // partial sums of this float4 for cells b-1, b, b+1
-        float pl = kx.k[0][0] * v.x + kx.k[1][0] * v.y + kx.k[2][0] * v.z + kx.k[3][0] * v.w;
-        const float pc = kx.k[0][1] * v.x + kx.k[1][1] * v.y + kx.k[2][1] * v.z + kx.k[3][1] * v.w;
-        float pr = kx.k[0][2] * v.x + kx.k[1][2] * v.y + kx.k[2][2] * v.z + kx.k[3][2] * v.w;
-        float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's contribution to my cell
-        float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's contribution to my cell
-        if (lane == 0) from_left = 0.f;
-        if (lane == 31) from_right = 0.f;
-        if (need_left) {
-          const float4 u = __ldcs(reinterpret_cast<const float4*>(row + 4 * (b - 1)));
-          from_left = kxl.k[0][2] * u.x + kxl.k[1][2] * u.y + kxl.k[2][2] * u.z + kxl.k[3][2] * u.w;
-        }
-        if (need_right) {
-          const float4 u = __ldcs(reinterpret_cast<const float4*>(row + 4 * (b + 1)));
-          from_right = kxr.k[0][0] * u.x + kxr.k[1][0] * u.y + kxr.k[2][0] * u.z + kxr.k[3][0] * u.w;
-        } else if (b == w - 1) {
-          from_right = 0.f;
-        }
+        const float pl = kx.k[0][0] * v[i].x + kx.k[1][0] * v[i].y + kx.k[2][0] * v[i].z + kx.k[3][0] * v[i].w;
+        const float pc = kx.k[0][1] * v[i].x + kx.k[1][1] * v[i].y + kx.k[2][1] * v[i].z + kx.k[3][1] * v[i].w;
+        const float pr = kx.k[0][2] * v[i].x + kx.k[1][2] * v[i].y + kx.k[2][2] * v[i].z + kx.k[3][2] * v[i].w;
+        const float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's share for my cell
+        const float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's share for my cell
         const float xr = (from_left + pc) + from_right;
         acc_prev = fmaf(ky.k[i][0], xr, acc_prev);
         acc_cur = fmaf(ky.k[i][1], xr, acc_cur);
         acc_next = fmaf(ky.k[i][2], xr, acc_next);
-        (void)pl, (void)pr;
       }
       // cell row a-1 has now received everything (block rows a-2 .. a)
-      if (live && a - 1 >= a0 && a - 1 < a1) gin[(p * h + (a - 1)) * (int64_t)w + b] = acc_prev;
+      if (owns && a - 1 >= a0 && a - 1 < a1) gin[(p * h + (a - 1)) * (int64_t)w + b] = acc_prev;
       acc_prev = acc_cur, acc_cur = acc_next, acc_next = 0.f;
     }
     // the last cell row of the strip when the strip ends at the image border
-    if (live && a1 == h && h - 1 >= a0) gin[(p * h + (h - 1)) * (int64_t)w + b] = acc_prev;
+    if (owns && a1 == h && h - 1 >= a0) gin[(p * h + (h - 1)) * (int64_t)w + b] = acc_prev;
   }
 }
 
@@ -337,15 +334,17 @@ extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, i
   ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   if (H == 4 * h && W == 4 * w && reinterpret_cast<uintptr_t>(gout) % 16 == 0) {
-    const int gx4 = (w + 127) / 128;
+    const int warps_x = (w + kBwdOwned - 1) / kBwdOwned;  // warps needed side by side
+    const int wpb = warps_x < 8 ? warps_x : 8;            // warps per block (exact cover when <= 8)
+    const int gx4 = (warps_x + wpb - 1) / wpb;
     int strip = 32;  // cell rows per thread strip: 2 halo block rows per strip (6 % extra reads)
     if (strip > h) strip = h;
     const int gy4 = (h + strip - 1) / strip;
-    int64_t gz4 = ((int64_t)sm_count() * 32 + (int64_t)gx4 * gy4 - 1) / ((int64_t)gx4 * gy4);
+    int64_t gz4 = ((int64_t)sm_count() * 16 + (int64_t)gx4 * gy4 - 1) / ((int64_t)gx4 * gy4);
     gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
     if (gz4 > 65535) gz4 = 65535;
-    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 128, 0, stream>>>(gout, gin, planes, h, w,
-                                                                             strip);
+    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 32 * wpb, 0, stream>>>(gout, gin, planes, h,
+                                                                                  w, strip);
     ROBSEG_LAUNCH_CHECK();
     return 0;
   }

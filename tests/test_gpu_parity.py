@@ -563,6 +563,47 @@ def test_fast_upsample_consumer_matches_stock(mods):
     assert rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
 
 
+def test_config1_scaled_upernet_gpu_vs_oracle_cpu(mods):
+    """BASELINE config 1 scaled down (UperNet-ConvNeXt-T_CVST random init, 21 classes, Mask-CE,
+    apgd_largereps n_iter=10 -> 3/3/4, eps 4/255, 2 images) on the GPU through the drop-in API vs the
+    CPU oracle driving the same weights.  Trajectories are chaotic across devices,
+    so the assert is on the metrics: per-image accuracy after the attack within 1.5 % absolute, same
+    loss level, perturbation inside the ball; the fast up-sampling path gives the same result class."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    C, S = 21, 96
+    torch.manual_seed(0)
+    model = mods.consumers.upernet_convnext("T", C).eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, S, S, generator=g)
+    with torch.no_grad():
+        y = model(x).argmax(1)
+    y = torch.where(torch.rand(2, S, S, generator=g) < 0.3, torch.randint(0, C, (2, S, S), generator=g), y)
+    noise = [2 * torch.rand(x.shape, generator=g) - 1 for _ in range(3)]
+    ox, ol, oacc = O.apgd_largereps(O.TorchModelAdapter(model), x.numpy(), y.numpy(), None, eps=4 / 255, n_iter=10,
+                                    loss="mask-ce-avg", early_stop=True, use_rs=True,
+                                    rand_ts=[n.numpy() for n in noise])
+    gm = mods.consumers.upernet_convnext("T", C)
+    gm.load_state_dict(model.state_dict())
+    gm = gm.to(dev()).eval()
+    real = torch.rand_like
+    for fast in (False, True):
+        gm.fast_upsample = fast
+        it = iter(noise)
+        torch.rand_like = lambda t, *a, **k: ((next(it) + 1) / 2).to(t.device)
+        try:
+            x_adv, lb, acc = mods.attacker.apgd_largereps(
+                gm, x.to(dev()), y.to(dev()), None, norm="Linf", eps=4 / 255, n_iter=10, loss="mask-ce-avg",
+                track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C)
+        finally:
+            torch.rand_like = real
+        assert float((x_adv.cpu() - x).abs().max()) <= 4 / 255 + 1e-6
+        assert np.abs(acc.cpu().numpy() - oacc).max() <= 0.015, (fast, acc.tolist(), oacc.tolist())
+        np.testing.assert_allclose(lb.cpu().numpy(), ol, rtol=0.05)
+    clean_acc = float((gm(x.to(dev())).argmax(1).cpu() == y).float().mean())
+    assert float(acc.mean()) < clean_acc - 0.05  # the attack did something
+
+
 def test_custom_ops_registered(mods):
     mods.ops.register_custom_ops()
     z, y, w = make_problem(1, 21, 16, 16, 5)
