@@ -122,10 +122,9 @@ def pixel_to_img_loss(loss, mask_background=None):
 
 def check_oscillation(x, j, k, y5, k3=0.75):
     """semseg/attacker.py:243-248 (kept for API parity; the attack uses the device version)."""
-    t = torch.zeros(x.shape[1]).to(x.device)
-    for counter5 in range(k):
-        t += (x[j - counter5] > x[j - counter5 - 1]).float()
-    return (t <= k * k3 * torch.ones_like(t)).float()
+    rows = [(j - c) % x.shape[0] for c in range(k + 1)]       # negative indices wrap (SURVEY 9-Q12)
+    ups = (x[rows[:-1]] > x[rows[1:]]).float().sum(0)           # increases inside the window
+    return (ups <= k * k3).float()
 
 
 def _ce(x, y, weights=None):  # accepts the third argument the caller passes (SURVEY 9-Q3)

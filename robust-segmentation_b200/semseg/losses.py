@@ -6,6 +6,8 @@ runs on the fused loss kernel: forward = one pass producing the per-pixel weight
 ``OhemCrossEntropy`` and ``Dice`` are not on the SEA / PIR-AT path (SURVEY.md section 2, row 4);
 they are kept as plain-PyTorch bodies for name compatibility only.
 """
+import math
+
 import torch
 from torch import Tensor, nn
 from torch.nn import functional as F
@@ -35,57 +37,63 @@ class CrossEntropy(nn.Module):
         return (wy * ce).sum() / wy.sum()
 
     def forward(self, preds, labels: Tensor) -> Tensor:
-        if isinstance(preds, tuple):
-            return sum([w * self._forward(pred, labels) for (pred, w) in zip(preds, self.aux_weights)])
-        return self._forward(preds, labels)
+        return _weighted_sum(self._forward, preds, labels, self.aux_weights)
+
+
+def _weighted_sum(fn, preds, labels, aux_weights):
+    """Main + auxiliary heads: preds may be a tuple (main, aux...) weighted by aux_weights."""
+    if isinstance(preds, tuple):
+        return sum(w * fn(p, labels) for p, w in zip(preds, aux_weights))
+    return fn(preds, labels)
 
 
 class OhemCrossEntropy(nn.Module):
-    """Unaccelerated (not on the hot path): same arithmetic as semseg/losses.py:30-63."""
+    """Online hard example mining CE (semseg/losses.py:30-63).  Not on the SEA / PIR-AT path; the
+    per-pixel CE comes from the fused kernel, the hard-example selection stays in PyTorch."""
 
     def __init__(self, ignore_label: int = 255, weight: Tensor = None, thresh: float = 0.7,
                  aux_weights: list = [1, 1]) -> None:
         super().__init__()
-        self.ignore_label = ignore_label
-        self.aux_weights = aux_weights
-        self.thresh = -torch.log(torch.tensor(thresh, dtype=torch.float))
-        self.criterion = nn.CrossEntropyLoss(weight=weight, ignore_index=ignore_label, reduction="none")
+        self.ignore_label, self.aux_weights, self.weight = ignore_label, aux_weights, weight
+        self.thresh = -math.log(thresh)
 
     def _forward(self, preds: Tensor, labels: Tensor) -> Tensor:
-        n_min = labels[labels != self.ignore_label].numel() // 16
-        loss = self.criterion(preds, labels).view(-1)
-        hard = loss[loss > self.thresh]
+        keep = labels != self.ignore_label
+        ce = ops.pixel_loss(preds, labels, "ce", None, self.ignore_label)
+        if self.weight is not None:
+            w = self.weight.to(preds.device, torch.float32)
+            ce = ce * w[labels.clamp(0, w.numel() - 1)] * keep
+        ce = ce.flatten()
+        n_min = int(keep.sum()) // 16
+        hard = ce[ce > self.thresh]
         if hard.numel() < n_min:
-            hard, _ = loss.topk(n_min)
-        return torch.mean(hard)
+            hard = ce.topk(n_min).values
+        return hard.mean()
 
     def forward(self, preds, labels: Tensor) -> Tensor:
-        if isinstance(preds, tuple):
-            return sum([w * self._forward(pred, labels) for (pred, w) in zip(preds, self.aux_weights)])
-        return self._forward(preds, labels)
+        return _weighted_sum(self._forward, preds, labels, self.aux_weights)
 
 
 class Dice(nn.Module):
-    """Unaccelerated (not on the hot path): same arithmetic as semseg/losses.py:66-93."""
+    """Dice / Tversky loss (semseg/losses.py:66-93; delta weighs FN against FP).  Not on the
+    SEA / PIR-AT path: plain PyTorch."""
 
     def __init__(self, delta: float = 0.5, aux_weights: list = [1, 0.4, 0.4]):
         super().__init__()
-        self.delta = delta
-        self.aux_weights = aux_weights
+        self.delta, self.aux_weights = delta, aux_weights
 
     def _forward(self, preds: Tensor, labels: Tensor) -> Tensor:
         n = preds.shape[1]
-        onehot = F.one_hot(labels, n).permute(0, 3, 1, 2)
-        tp = torch.sum(onehot * preds, dim=(2, 3))
-        fn = torch.sum(onehot * (1 - preds), dim=(2, 3))
-        fp = torch.sum((1 - onehot) * preds, dim=(2, 3))
+        onehot = F.one_hot(labels, n).movedim(-1, 1).to(preds.dtype)
+        dims = tuple(range(2, preds.dim()))
+        tp = (onehot * preds).sum(dims)
+        fn = (onehot * (1 - preds)).sum(dims)
+        fp = ((1 - onehot) * preds).sum(dims)
         score = (tp + 1e-6) / (tp + self.delta * fn + (1 - self.delta) * fp + 1e-6)
-        return (torch.sum(1 - score, dim=-1) / n).mean()
+        return ((1 - score).sum(-1) / n).mean()
 
     def forward(self, preds, targets: Tensor) -> Tensor:
-        if isinstance(preds, tuple):
-            return sum([w * self._forward(pred, targets) for (pred, w) in zip(preds, self.aux_weights)])
-        return self._forward(preds, targets)
+        return _weighted_sum(self._forward, preds, targets, self.aux_weights)
 
 
 __all__ = ["CrossEntropy", "OhemCrossEntropy", "Dice"]

@@ -42,28 +42,27 @@ class Metrics:
         ops.pixel_hist(am, target, self.num_classes, self.ignore_label, hist_total=self.hist_int,
                        want_counts=False)
 
+    # ---- finalisers: float32 arithmetic in the reference's order (semseg/metrics.py:35-60) ----
+    @staticmethod
+    def _percent(per_class: Tensor):
+        """(per-class list, NaN-skipping mean), both x100 and rounded to 2 decimals."""
+        mean = per_class[~per_class.isnan()].mean().item() * 100
+        return (per_class * 100).cpu().numpy().round(2).tolist(), round(mean, 2)
+
+    def _marginals(self):
+        h = self.hist
+        return h.diag(), h.sum(0), h.sum(1)
+
     def compute_iou(self):
-        hist = self.hist.clone()
-        ious = hist.diag() / (hist.sum(0) + hist.sum(1) - hist.diag())
-        miou = ious[~ious.isnan()].mean().item()
-        ious *= 100
-        miou *= 100
-        return ious.cpu().numpy().round(2).tolist(), round(miou, 2)
+        tp, pred_total, target_total = self._marginals()
+        return self._percent(tp / (pred_total + target_total - tp))
 
     def compute_f1(self):
-        hist = self.hist.clone()
-        f1 = 2 * hist.diag() / (hist.sum(0) + hist.sum(1))
-        mf1 = f1[~f1.isnan()].mean().item()
-        f1 *= 100
-        mf1 *= 100
-        return f1.cpu().numpy().round(2).tolist(), round(mf1, 2)
+        tp, pred_total, target_total = self._marginals()
+        return self._percent(2 * tp / (pred_total + target_total))
 
     def compute_pixel_acc(self):
-        hist = self.hist.clone()
-        acc = hist.diag() / hist.sum(1)
-        aAcc = hist.diag().sum() / hist.sum()
-        macc = acc[~acc.isnan()].mean().item()
-        acc *= 100
-        macc *= 100
-        aAcc *= 100
-        return (acc.cpu().numpy().round(2).tolist(), round(macc, 2), aAcc.cpu().numpy().round(2))
+        tp, _, target_total = self._marginals()
+        per_class, macc = self._percent(tp / target_total)
+        overall = (tp.sum() / self.hist.sum()) * 100
+        return per_class, macc, overall.cpu().numpy().round(2)

@@ -19,18 +19,15 @@ from .. import ops
 
 
 def check_imgs(adv, x, norm, verbose=False):
-    delta = (adv - x).view(adv.shape[0], -1)
-    if norm == "Linf":
-        res = delta.abs().max(dim=1)[0]
-    elif norm == "L2":
-        res = (delta ** 2).sum(dim=1).sqrt()
-    elif norm == "L1":
-        res = delta.abs().sum(dim=1)
-    str_det = (f"max {norm} pert: {res.max():.5f}, nan in imgs: {(adv != adv).sum()}, "
-               f"max in imgs: {adv.max():.5f}, min in imgs: {adv.min():.5f}")
+    """Perturbation-size / range report of an adversarial batch (tools/infer.py:39-53)."""
+    flat = (adv - x).flatten(1)
+    size = {"Linf": lambda d: d.abs().amax(1), "L2": lambda d: d.square().sum(1).sqrt(),
+            "L1": lambda d: d.abs().sum(1)}[norm](flat)
+    report = (f"max {norm} pert: {size.max():.5f}, nan in imgs: {adv.isnan().sum()}, "
+              f"max in imgs: {adv.max():.5f}, min in imgs: {adv.min():.5f}")
     if verbose:
-        print(str_det)
-    return str_det
+        print(report)
+    return report
 
 
 def eval_performance(model, data_loader, n_batches=-1, n_cls=21, return_output=False,

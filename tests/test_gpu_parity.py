@@ -604,6 +604,56 @@ def test_config1_scaled_upernet_gpu_vs_oracle_cpu(mods):
     assert float(acc.mean()) < clean_acc - 0.05  # the attack did something
 
 
+def test_ohem_and_dice_name_compat(mods):
+    """OhemCrossEntropy / Dice are off the hot path (kept for get_loss name parity): same values as
+    the formulas of semseg/losses.py:30-93 written with stock torch ops."""
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(3)
+    C = 6
+    z = torch.randn(2, C, 20, 20, generator=g).to(dev())
+    y = torch.randint(0, C, (2, 20, 20), generator=g).to(dev())
+    y[0, :2] = 255
+    ours = mods.losses.get_loss("OhemCrossEntropy", 255, None)(z, y)
+    ce = F.cross_entropy(z, y, ignore_index=255, reduction="none").view(-1)
+    n_min = int((y != 255).sum()) // 16
+    hard = ce[ce > -torch.log(torch.tensor(0.7))]
+    ref = (hard if hard.numel() >= n_min else ce.topk(n_min)[0]).mean()
+    assert torch.allclose(ours, ref, rtol=1e-5)
+    p = z.softmax(1)
+    yy = y.clamp(max=C - 1)
+    ours = mods.losses.get_loss("Dice")(p, yy)
+    oh = F.one_hot(yy, C).permute(0, 3, 1, 2)
+    tp, fn, fp = (oh * p).sum((2, 3)), (oh * (1 - p)).sum((2, 3)), ((1 - oh) * p).sum((2, 3))
+    ref = ((1 - (tp + 1e-6) / (tp + 0.5 * fn + 0.5 * fp + 1e-6)).sum(-1) / C).mean()
+    assert torch.allclose(ours, ref, rtol=1e-5)
+    assert isinstance(mods.losses.get_loss("CrossEntropy", -1, None), mods.losses.CrossEntropy)
+
+
+def test_pirat_training_step_flow(mods):
+    """tools/train_rob_seg.py:326-352 with the drop-in attack: zero_grad -> eval-mode 2-step PGD
+    (parameter grads accumulate) -> train-mode loss -> backward -> optimizer step."""
+    torch.manual_seed(0)
+    C = 8
+    model = mods.consumers.upernet_convnext("T", C).to(dev())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(2, 3, 64, 64, generator=g).to(dev())
+    lbl = torch.randint(0, C, (2, 64, 64), generator=g).to(dev())
+    attack = mods.val.Pgd_Attack_1(epsilon=4 / 255, alpha=1e-2, num_iter=2, los="pgd")
+    for fast in (False, True):
+        opt.zero_grad(set_to_none=True)
+        model.eval()
+        adv = attack.adv_attack(model, img, lbl)[0] if not fast else \
+            mods.val.Pgd_Attack_1(epsilon=4 / 255, num_iter=2, los="pgd", input_grad_only=True).adv_attack(model, img, lbl)[0]
+        model.train()
+        attack_grads = [p.grad is not None for p in model.backbone.parameters()]
+        assert all(attack_grads) != fast and any(attack_grads) != fast
+        loss, _ = model(adv, lbl)
+        loss.backward()
+        opt.step()
+        assert torch.isfinite(loss) and float((adv - img).abs().max()) <= 4 / 255 + 1e-6
+
+
 def test_custom_ops_registered(mods):
     mods.ops.register_custom_ops()
     z, y, w = make_problem(1, 21, 16, 16, 5)
