@@ -549,6 +549,62 @@ __global__ void __launch_bounds__(G == 2 ? 1024 : 512, 1)
 }
 
 // ---- generic path: any shape / alignment ---------------------------------------------------
+// Shapes a tensor map cannot describe (HW*sizeof(T) not a multiple of 16 B -- e.g. the
+// reference's 473x473 PASCAL-VOC crops -- or C > 256).  Each warp owns K stages of
+// [C][32] elements and fills them with 4-byte cp.async copies (SASS LDGSTS: no register
+// staging, a whole tile in flight per warp), double-buffered when shared memory allows, then
+// runs the same per-tile code.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 4 : 0;  // src-size 0: zero-fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(n)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams p, const int K) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int stage_elems = p.C * 32;
+  float* bufs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * K * stage_elems;
+  const float* logits = reinterpret_cast<const float*>(p.logits);
+  auto issue = [&](int tile, float* dst) {
+    const int b = tile / p.tiles_per_img;
+    const int64_t px = (int64_t)(tile - b * p.tiles_per_img) * 32 + lane;
+    const bool inb = px < p.HW;
+    const float* src = logits + (int64_t)b * p.C * p.HW + (inb ? px : 0);
+    for (int c = 0; c < p.C; ++c) cp_async4(dst + c * 32 + lane, src + (int64_t)c * p.HW, inb);
+    cp_async_commit();
+  };
+  const int stride = gridDim.x * W;
+  int tile = blockIdx.x * W + warp;
+  int k = 0;
+  if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
+  for (; tile < p.num_tiles; tile += stride) {
+    float* cur = bufs + (size_t)k * stage_elems;
+    if (K == 2) {
+      const int next = tile + stride;
+      if (next < p.num_tiles) {
+        issue(next, bufs + (size_t)(k ^ 1) * stage_elems);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      k ^= 1;
+    } else {
+      issue(tile, cur);
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{});
+    __syncwarp();
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -616,7 +672,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // ring + barriers + alignment slack
 
-static int pick_vec(int C, int esize) {
+static int pick_vec(int C, int esize, bool with_grad) {
   // widest per-lane vector whose stage ([C][32*VEC] elements) stays <= 40 KB, so at least 5
   // consumer warps fit; per-lane bytes are capped at 16.  Wider rows matter: measured on B200
   // at C=150 the 128 B-row layout tops out near 5.1 TB/s, 256 B rows reach 5.6 TB/s
@@ -624,7 +680,8 @@ static int pick_vec(int C, int esize) {
   const int max_vec = 16 / esize;
   int vec = max_vec;
   // bf16 pays an unpack per element, so it keeps the smaller (<= 24 KB, more warps) stages.
-  const size_t cap = esize == 2 ? 24 * 1024 : 40 * 1024;
+  // Loss-only / argmax launches have no store stream and are warp-count bound: smaller stages.
+  const size_t cap = (esize == 2 || !with_grad) ? 24 * 1024 : 40 * 1024;
   while (vec > (esize == 2 ? 2 : 1) && (size_t)C * 32 * vec * esize > cap) vec >>= 1;
   if (const char* e = getenv("ROBSEG_LOSS_VEC")) {
     const int v = atoi(e);
@@ -705,6 +762,26 @@ static int launch_generic(const LossParams& p0, cudaStream_t stream) {
   p.num_tiles = p.B * p.tiles_per_img;
   const size_t stage = (size_t)p.C * 32 * sizeof(T);
   ROBSEG_REQUIRE(stage <= kSmemBudget, "C=%d too large for one shared-memory stage", p.C);
+  if constexpr (sizeof(T) == 4) {
+    // as many warps per SM as shared memory allows (<= 64), two stages per warp when they fit
+    int warps_sm = (int)(kSmemBudget / stage);
+    if (warps_sm > 64) warps_sm = 64;
+    int K = (size_t)2 * stage * (warps_sm >= 32 ? 32 : warps_sm) <= kSmemBudget && warps_sm >= 16 ? 2 : 1;
+    if (K == 2) warps_sm = (int)(kSmemBudget / (2 * stage)) > 64 ? 64 : (int)(kSmemBudget / (2 * stage));
+    int W = warps_sm >= 8 ? 8 : warps_sm;  // warps per CTA
+    int ctas_sm = warps_sm / W;
+    if (ctas_sm < 1) ctas_sm = 1;
+    const size_t smem = (size_t)W * K * stage;
+    ROBSEG_CUDA(cudaFuncSetAttribute(loss_generic_f32_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count() * ctas_sm;
+    const int max_useful = (p.num_tiles + W - 1) / W;
+    if (grid > max_useful) grid = max_useful;
+    if (grid < 1) grid = 1;
+    loss_generic_f32_kernel<<<grid, 32 * W, smem, stream>>>(p, K);
+    ROBSEG_LAUNCH_CHECK();
+    return 0;
+  }
   int W = (int)(kSmemBudget / 2 / stage);  // aim for two CTAs per SM
   if (W > 8) W = 8;
   if (W < 1) W = 1;
@@ -765,7 +842,7 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
   int rc;
   int tiles_per_img;
   if (tma_ok) {
-    const int vec = pick_vec(C, esize);
+    const int vec = pick_vec(C, esize, dlogits != nullptr);
     tiles_per_img = (int)((HW + 32 * vec - 1) / (32 * vec));
     if (dtype == ROBSEG_F32) {
       rc = vec == 4 ? launch_tma_pick<float, 4>(p, stream)
