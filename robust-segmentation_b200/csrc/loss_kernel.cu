@@ -842,7 +842,8 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
   int rc;
   int tiles_per_img;
   if (tma_ok) {
-    const int vec = pick_vec(C, esize, dlogits != nullptr);
+    // (argmax-only launches are pure streaming reads: wide rows again)
+    const int vec = pick_vec(C, esize, dlogits != nullptr || loss_kind == ROBSEG_LOSS_ARGMAX);
     tiles_per_img = (int)((HW + 32 * vec - 1) / (32 * vec));
     if (dtype == ROBSEG_F32) {
       rc = vec == 4 ? launch_tma_pick<float, 4>(p, stream)

@@ -171,3 +171,38 @@ def test_allreduce_counters_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()  # (stdout of the ranks interleaves)
+
+
+def test_dropin_rebinds_reference_names(mods, tmp_path, monkeypatch):
+    """dropin.install() against a stand-in checkout: the names SURVEY 8b lists are rebound to the
+    B200 implementations, everything else in the reference package is left alone."""
+    from importlib import import_module
+
+    root = tmp_path / "Robust-Segmentation"
+    (root / "semseg").mkdir(parents=True)
+    (root / "tools").mkdir()
+    (root / "semseg" / "__init__.py").write_text("MODELS = 'theirs'\n")
+    (root / "semseg" / "attacker.py").write_text("def apgd_largereps(*a, **k):\n    return 'reference'\n")
+    (root / "semseg" / "val.py").write_text("class Pgd_Attack: pass\nclass Pgd_Attack_1: pass\n"
+                                            "def evaluate(): return 'reference'\nKEEP = 1\n")
+    (root / "semseg" / "metrics.py").write_text("class Metrics: pass\n")
+    (root / "semseg" / "losses.py").write_text("class CrossEntropy: pass\ndef get_loss(): pass\n")
+    (root / "tools" / "__init__.py").write_text("")
+    (root / "tools" / "worse_only.py").write_text("class evalSEA: pass\n")
+    for name in [n for n in sys.modules if n == "semseg" or n.startswith("semseg.") or n == "tools" or n.startswith("tools.")]:
+        monkeypatch.delitem(sys.modules, name)
+    monkeypatch.syspath_prepend(str(root))
+    dropin = import_module("robseg_b200.dropin")
+    dropin.install(str(root))
+    import semseg
+    import semseg.attacker as ref_attacker
+    import semseg.val as ref_val
+    import tools.worse_only as ref_sea
+
+    assert semseg.MODELS == "theirs" and ref_val.KEEP == 1
+    assert ref_attacker is mods.attacker and semseg.attacker is mods.attacker
+    assert ref_val.Pgd_Attack is mods.val.Pgd_Attack and ref_val.evaluate is mods.val.evaluate
+    assert import_module("semseg.metrics").Metrics is mods.metrics.Metrics
+    assert ref_sea.evalSEA is mods.worse.evalSEA
+    for name in [n for n in sys.modules if n == "semseg" or n.startswith("semseg.") or n == "tools" or n.startswith("tools.")]:
+        monkeypatch.delitem(sys.modules, name)
