@@ -612,6 +612,42 @@ def test_config1_scaled_upernet_gpu_vs_oracle_cpu(mods):
     assert float(acc.mean()) < clean_acc - 0.05  # the attack did something
 
 
+def test_infer_evaluate_and_eval_performance_flow(mods):
+    """tools/infer.py:136-155 + :56-133 mirrors: attack every batch, keep (x_adv, target) pairs on the
+    host (pinned, async) or on the device, then score the adversarial "loader"."""
+    from functools import partial
+
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        C = 7
+        model = mods.consumers.TinySegNet(C, seed=6).to(dev()).eval()
+        g = torch.Generator().manual_seed(2)
+        loader = []
+        for _ in range(3):
+            x = torch.rand(2, 3, 24, 24, generator=g)
+            with torch.no_grad():
+                y = model(x.to(dev())).argmax(1).cpu()
+            loader.append((x, y, ["a", "b"]))
+        attack_fn = partial(mods.attacker.apgd_largereps, norm="Linf", eps=8 / 255, n_iter=6, n_restarts=1,
+                            use_rs=True, loss="mask-ce-avg", track_loss="ce-avg", num_classes=C, early_stop=True)
+        args = type("A", (), {"norm": "Linf"})()
+        torch.manual_seed(0)
+        adv_host = mods.infer.evaluate(loader, model, attack_fn, n_batches=-1, args=args, weights=None)
+        torch.manual_seed(0)
+        adv_dev = mods.infer.evaluate(loader, model, attack_fn, n_batches=2, args=args, weights=None, keep_on_device=True)
+        assert len(adv_host) == 3 and len(adv_dev) == 2
+        for (xh, th), (xd, td), (x, y, _) in zip(adv_host, adv_dev, loader):
+            assert not xh.is_cuda and xh.is_pinned() and xd.is_cuda
+            assert torch.equal(xh, xd.cpu()) and torch.equal(th, y)
+            assert float((xh - x).abs().max()) <= 8 / 255 + 1e-6
+        clean, _ = mods.infer.eval_performance(model, loader, n_cls=C)
+        stats, l_out = mods.infer.eval_performance(model, adv_host, n_cls=C)
+        assert l_out.shape == (6, 24, 24) and clean["aAcc"] == 1.0 and stats["aAcc"] < 0.9
+    finally:
+        torch.backends.cudnn.deterministic = det
+
+
 def test_ohem_and_dice_name_compat(mods):
     """OhemCrossEntropy / Dice are off the hot path (kept for get_loss name parity): same values as
     the formulas of semseg/losses.py:30-93 written with stock torch ops."""
