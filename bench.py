@@ -367,10 +367,11 @@ def run_micro(args, mods, dev, rank, world):
     ys = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.8, torch.full_like(y, 3), y)  # 80 % one class
     ps = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.7, ys, pred)
     time_it("pixel_hist/counts skewed-80pct", lambda: ops.pixel_hist(ps, ys, C), 16 * y.numel())
-    blk = torch.randint(0, C, (B, S // 32, S // 32), device=dev, generator=g)  # 32x32 constant regions
-    yc = blk.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
-    pc = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.9, yc, pred)
-    time_it("pixel_hist/counts coherent-32x32", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel())
+    blk = torch.randint(0, C, (B, S // 64, S // 64), device=dev, generator=g)  # 64x64 constant regions
+    yc = blk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()
+    pblk = torch.where(torch.rand(blk.shape, device=dev, generator=g) < 0.7, blk, torch.randint_like(blk, C))
+    pc = pblk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()  # region-wise right / wrong
+    time_it("pixel_hist/counts piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel())
     if args.micro_dtype == "fp32":
         import torch.nn.functional as F
 
