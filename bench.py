@@ -386,17 +386,61 @@ def run_micro(args, mods, dev, rank, world):
         up = F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False)
         time_it("upsample_bwd x4 (ATen)", lambda: torch.autograd.grad(up, [lr], grad_outputs=gup, retain_graph=True), nb)
         del up, lr, low, gup
-    # the stock ATen chain of the reference on the same device (SURVEY 8d "also report")
+    # the stock ATen op chains of the reference on the same device (SURVEY 8d "also report"):
+    # what the fused kernels replace, timed on identical inputs
     if args.micro_dtype == "fp32" and B <= 16:
         import torch.nn.functional as F
 
-        def aten_maskce():
+        def aten_maskce():  # semseg/attacker.py:143-152,237-240 + autograd.grad
             zz = z.detach().requires_grad_()
             mask = (zz.max(1)[1] == y) * (y != -1)
             l = (mask.float().detach() * F.cross_entropy(zz, y, reduction="none", ignore_index=-1))
             torch.autograd.grad(l.view(B, -1).mean(-1).sum(), [zz])
 
-        time_it("aten_chain/mask-ce-avg", aten_maskce, 2 * z.numel() * es + 8 * y.numel())
+        def aten_js():  # semseg/attacker.py:187-234
+            zz = z.detach().requires_grad_()
+            p_ = F.softmax(zz, 1)
+            q_ = F.one_hot(y.view(B, -1), C).permute(0, 2, 1).view(p_.shape).float()
+            m_ = (p_ + q_) / 2
+            l = ((F.kl_div(m_.log(), p_, reduction="none") + F.kl_div(m_.log(), q_, reduction="none")) / 2).sum(1)
+            torch.autograd.grad(l.view(B, -1).mean(-1).sum(), [zz])
+
+        def aten_track_and_acc():  # :353-361,370-373,485-490: second log-softmax + two more max(1)
+            F.cross_entropy(z, y, reduction="none", ignore_index=-1).view(B, -1).mean(-1)
+            (z.max(1)[1] == y).float().view(B, -1).mean(-1)
+            z.max(1)[1]
+
+        def aten_step():  # :388-410
+            eps, a = 8 / 255, 0.75
+            st = step.view(-1, 1, 1, 1)
+            g2 = xa - xo
+            x1 = xa + st * torch.sign(gr)
+            x1 = torch.clamp(torch.min(torch.max(x1, x - eps), x + eps), 0.0, 1.0)
+            torch.clamp(torch.min(torch.max(xa + (x1 - xa) * a + g2 * (1 - a), x - eps), x + eps), 0.0, 1.0)
+
+        def aten_iou_acc():  # compute_iou_acc, :9-52: 2*C masked reductions + 3 host syncs
+            acc_cls, n_pxl = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            int_cls, uni = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            hit = pred == y
+            for cl in range(C):
+                ind = y == cl
+                acc_cls[cl] += (hit * ind).float().sum()
+                n_pxl[cl] += ind.float().sum()
+            (acc_cls[n_pxl > 0] / n_pxl[n_pxl > 0]).mean().cpu()
+            (acc_cls.sum() / n_pxl.sum()).cpu()
+            for cl in range(C):
+                ind = y == cl
+                s_ = hit[ind].float().sum()
+                int_cls[cl] += s_
+                uni[cl] += ind.float().sum() + (pred == cl).float().sum() - s_
+            (int_cls[uni > 0] / uni[uni > 0]).mean().cpu()
+
+        nb = 2 * z.numel() * es + 8 * y.numel()
+        time_it("ATen chain: mask-ce-avg loss+grad", aten_maskce, nb)
+        time_it("ATen chain: js-avg loss+grad", aten_js, nb)
+        time_it("ATen chain: track CE + accuracy + argmax", aten_track_and_acc, 0)
+        time_it("ATen chain: APGD step", aten_step, 20 * x.numel())
+        time_it("ATen chain: compute_iou_acc", aten_iou_acc, 16 * y.numel())
     if rank == 0:
         k = res["loss_grad/mask-ce-avg"]
         print(json.dumps({
