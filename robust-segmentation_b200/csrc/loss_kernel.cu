@@ -577,7 +577,12 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
     const int64_t px = (int64_t)(tile - b * p.tiles_per_img) * 32 + lane;
     const bool inb = px < p.HW;
     const float* src = logits + (int64_t)b * p.C * p.HW + (inb ? px : 0);
-    for (int c = 0; c < p.C; ++c) cp_async4(dst + c * 32 + lane, src + (int64_t)c * p.HW, inb);
+    uint32_t d = smem_u32(dst + lane);
+    const int n = inb ? 4 : 0;  // src-size 0: zero-fill
+    const int64_t hw = p.HW;
+#pragma unroll 4
+    for (int c = 0; c < p.C; ++c, src += hw, d += 128)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
     cp_async_commit();
   };
   const int stride = gridDim.x * W;
@@ -600,7 +605,11 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
       cp_async_wait<0>();
     }
     __syncwarp();
-    process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{});
+    const int tin = tile % p.tiles_per_img;
+    if ((int64_t)(tin + 1) * 32 <= p.HW)
+      process_tile<float, 1, 1, false>(p, cur, tile, lane, 0, PairXch{});
+    else
+      process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{});
     __syncwarp();
   }
 }
