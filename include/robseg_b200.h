@@ -151,7 +151,9 @@ int robseg_apgd_bookkeep(const int32_t* correct, const int32_t* valid, const flo
  * Flag-driven row copies (the boolean-index assignments of semseg/attacker.py:494-495,
  * 523-525,547-548) in one launch: for each job j and row b, if flags[j][b] != 0 (and, when
  * unless[j] != NULL, unless[j][b] == 0) copy row_bytes[j] bytes dst[j][b] <- src[j][b].
- * Up to ROBSEG_MAX_ROW_JOBS jobs; row sizes must be multiples of 4 bytes.
+ * Up to ROBSEG_MAX_ROW_JOBS jobs; row sizes must be multiples of 4 bytes.  Jobs of one call run
+ * concurrently: no job may write a buffer another job of the same call reads (the APGD restart
+ * copies x_adv <- x_best therefore go in a second call, after x_best_adv <- x_adv).
  */
 #define ROBSEG_MAX_ROW_JOBS 8
 typedef struct {

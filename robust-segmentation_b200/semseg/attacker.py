@@ -279,9 +279,13 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
                 (grad_best, grad, flags[1], None)]
         if keep_pred:
             jobs.append((pred_best, out.pred, flags[0], None))
-        if i in checks:  # restart the halved rows from their best point (:546-548)
-            jobs += [(x_adv, x_best, flags[2], flags[1]), (grad, grad_best, flags[2], flags[1])]
         ops.row_select(jobs, bs, device)
+        if i in checks:
+            # restart the halved rows from their best point (:546-548).  A separate launch: these
+            # jobs WRITE x_adv, which the x_best_adv job above reads for the same row when the
+            # accuracy improved but the loss did not -- stream order keeps the reference's sequence.
+            ops.row_select([(x_adv, x_best, flags[2], flags[1]), (grad, grad_best, flags[2], flags[1])],
+                           bs, device)
 
         if verbose:
             m_acc, a_acc, m_iou = compute_iou_acc(pred_best, y, n_cls, ignore_index=ignore_index)

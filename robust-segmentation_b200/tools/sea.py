@@ -1,0 +1,85 @@
+"""Device-resident SEA driver: the ``__main__`` loop of the reference's ``tools/infer.py``
+(:332-403) for the part that sits on the hot path, with the B200 bookkeeping.
+
+    stats = run_sea(model, loader, n_cls, eps=8/255, n_iter=300, weights=bal_weights)
+
+For every batch: the three SEA attacks (``mask-ce-bal``, ``mask-ce-avg``, ``js-avg``) through
+``apgd_largereps``; the argmax map of each adversarial point comes back from the attack
+(``return_pred``) instead of a D2H copy of ``x_adv`` + a later re-forward (tools/infer.py:151,82-90);
+exact int64 per-image counters are accumulated on the device (``robseg_pixel_hist``).  With
+``torch.distributed`` initialised every rank attacks its own contiguous shard of the loader's batches
+and ONE int64 all-reduce merges the counters.  The aggregation is the same
+code path as ``evalSEA``: per-attack mAcc / aAcc / mIoU (float32 finaliser of tools/infer.py:99-116),
+image-wise worst aACC (tools/worse_only.py:396-408) and the greedy worst-case mIoU (:267-334).
+"""
+import random
+
+import torch
+import torch.distributed as dist
+
+from .. import dist as rdist
+from .. import ops
+from ..semseg import attacker
+from .infer import _finalize
+from .worse_only import SEED, greedy_worst_miou
+
+LOSSES = ("mask-ce-bal", "mask-ce-avg", "js-avg")
+
+
+def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, losses=LOSSES,
+            n_batches=-1, device="cuda", keep_adv=False, group=None):
+    """Returns a dict: ``clean`` and per-loss ``{mAcc,aAcc,mIoU}``, ``worst_Acc``,
+    ``worst_Acc_indiv`` [A], ``final_miou``, ``n_images`` (+ ``x_adv`` per loss if keep_adv)."""
+    model.eval()
+    dev = torch.device(device)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    batches = []
+    for i, vals in enumerate(loader):
+        batches.append((vals[0], vals[1]))
+        if i + 1 == n_batches:
+            break
+    sizes = [b[0].shape[0] for b in batches]
+    n_total = sum(sizes)
+    lo_b, hi_b = rdist.shard_range(len(batches), rank, world)
+    img_lo = sum(sizes[:lo_b])
+    A = len(losses)
+    per_loss = [[] for _ in range(A)]   # per batch [3, B, C] counters for every attack
+    clean_cnt = []
+    advs = [[] for _ in range(A)]
+    for x, y in batches[lo_b:hi_b]:
+        x = x.to(dev, non_blocking=True)
+        y = y.to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = model(x)
+        if out.dtype not in (torch.float32, torch.bfloat16):
+            out = out.float()
+        p0 = ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred
+        c = ops.pixel_hist(p0, y, n_cls)
+        clean_cnt.append(torch.stack([c["inter"], c["tgt"], c["prd"]]))
+        del out
+        for a, loss in enumerate(losses):
+            x_adv, _, _, pred = attacker.apgd_largereps(
+                model, x, y, weights, norm="Linf", eps=eps, n_iter=n_iter, loss=loss, track_loss="ce-avg",
+                use_rs=True, early_stop=True, num_classes=n_cls, return_pred=True)
+            c = ops.pixel_hist(pred, y, n_cls)
+            per_loss[a].append(torch.stack([c["inter"], c["tgt"], c["prd"]]))
+            if keep_adv:
+                advs[a].append(x_adv)
+    zero = torch.zeros((3, 0, n_cls), dtype=torch.int64, device=dev)
+    local = torch.stack([torch.cat(pl, 1) if pl else zero for pl in per_loss] +
+                        [torch.cat(clean_cnt, 1) if clean_cnt else zero], 1)   # [3, A+1, n_local, C]
+    inter, tgt, prd, _ = rdist.allreduce_counters(n_total, img_lo, local[0], local[1], local[2], group=group)
+    res = {"n_images": n_total, "clean": _finalize(inter[A].sum(0), tgt[A].sum(0), prd[A].sum(0))}
+    for a, loss in enumerate(losses):
+        res[loss] = _finalize(inter[a].sum(0), tgt[a].sum(0), prd[a].sum(0))
+    acc_an, _ = ops.sea_worst_acc(inter[:A].contiguous(), tgt[:A].contiguous())
+    acc_an = acc_an.cpu()
+    res["worst_Acc"] = acc_an.min(0)[0].mean().item()
+    res["worst_Acc_indiv"] = acc_an.mean(-1)
+    union = (tgt + prd - inter)[:A]
+    random.seed(SEED)
+    res["final_miou"], res["selected_attack"] = greedy_worst_miou(inter[:A].cpu().numpy(), union.cpu().numpy())
+    if keep_adv:
+        res["x_adv"] = {loss: torch.cat(advs[a]) if advs[a] else None for a, loss in enumerate(losses)}
+    return res

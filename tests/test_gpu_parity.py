@@ -256,10 +256,9 @@ def test_bookkeeping_teacher_forced(mods):
         xa, gr = t(x_i), t(g_i)
         mods.ops.apgd_bookkeep(t(correct, torch.int32), t(valid, torch.int32), t(loss), acc, lb, lbl,
                                red, step, ls, i, checks.get(i, 0), HW, False, flags, done)
-        jobs = [(xba, xa, flags[0], None), (xb, xa, flags[1], None), (gb, gr, flags[1], None)]
-        if i in checks:
-            jobs += [(xa, xb, flags[2], flags[1]), (gr, gb, flags[2], flags[1])]
-        mods.ops.row_select(jobs, B, dev())
+        mods.ops.row_select([(xba, xa, flags[0], None), (xb, xa, flags[1], None), (gb, gr, flags[1], None)], B, dev())
+        if i in checks:  # second launch: the restart writes x_adv, which the first launch reads
+            mods.ops.row_select([(xa, xb, flags[2], flags[1]), (gr, gb, flags[2], flags[1])], B, dev())
         for name, d_, o_ in (("acc", acc, st.acc), ("loss_best", lb, st.loss_best), ("step", step, st.step),
                              ("x_best", xb, st.x_best), ("x_best_adv", xba, st.x_best_adv),
                              ("grad_best", gb, st.grad_best), ("x_adv", xa, st.x_adv), ("grad", gr, st.grad)):
@@ -644,6 +643,47 @@ def test_infer_evaluate_and_eval_performance_flow(mods):
         clean, _ = mods.infer.eval_performance(model, loader, n_cls=C)
         stats, l_out = mods.infer.eval_performance(model, adv_host, n_cls=C)
         assert l_out.shape == (6, 24, 24) and clean["aAcc"] == 1.0 and stats["aAcc"] < 0.9
+    finally:
+        torch.backends.cudnn.deterministic = det
+
+
+def test_run_sea_driver_matches_evalsea(mods, tmp_path):
+    """tools/sea.run_sea (device-resident bookkeeping) == the reference-shaped flow: attack, re-forward the
+    adversarial batches with eval_performance, aggregate with evalSEA."""
+    from importlib import import_module
+
+    sea = import_module("robseg_b200.tools.sea")
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        C = 6
+        model = mods.consumers.TinySegNet(C, seed=8).to(dev()).eval()
+        g = torch.Generator().manual_seed(4)
+        loader = []
+        for _ in range(2):
+            x = torch.rand(3, 3, 20, 20, generator=g)
+            with torch.no_grad():
+                y = model(x.to(dev())).argmax(1).cpu()
+            y[0, :2] = -1
+            loader.append((x, y, ["n"] * 3))
+        torch.manual_seed(7)
+        res = sea.run_sea(model, loader, C, eps=8 / 255, n_iter=8, keep_adv=True)
+        assert res["n_images"] == 6 and res["clean"]["aAcc"] == 1.0
+        l_outs = []
+        for loss in sea.LOSSES:
+            xa = res["x_adv"][loss]
+            adv_loader = [(xa[:3].cpu(), loader[0][1]), (xa[3:].cpu(), loader[1][1])]
+            stats, l_out = mods.infer.eval_performance(model, adv_loader, n_cls=C)
+            assert stats == res[loss]
+            l_outs.append(l_out)
+        targets = torch.cat([b[1] for b in loader])
+        sd = {}
+        ev = mods.worse.evalSEA(targets, l_outs, 8, C, "x", str(tmp_path), sd, "m", device=dev())
+        ev.worse_case_eval(bs=3)
+        random.seed(225)
+        ev.worst_case_miou()
+        assert sd["worst_Acc"] == res["worst_Acc"] and sd["final_miou"] == res["final_miou"]
+        assert torch.equal(sd["worst_Acc_indiv"], res["worst_Acc_indiv"])
     finally:
         torch.backends.cudnn.deterministic = det
 
