@@ -275,6 +275,40 @@ def test_bookkeeping_teacher_forced(mods):
     assert torch.equal(lb, before + 1) and int(flags.abs().sum()) == 0
 
 
+def test_restart_copy_does_not_race_with_best_adv_copy(mods):
+    """Accuracy improves (x_best_adv <- x_adv) while the loss does not and the step is halved
+    (x_adv <- x_best) for the SAME rows: the reference does these sequentially (attacker.py:494,547);
+    large rows so that the copies span many thread blocks."""
+    B, D, HW = 6, 3 * 512 * 512, 100
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x_adv = torch.rand(B, D, device=dev(), generator=g)
+    x_best = torch.rand(B, D, device=dev(), generator=g)
+    grad, grad_best = torch.randn(B, D, device=dev(), generator=g), torch.randn(B, D, device=dev(), generator=g)
+    x_best_adv = torch.zeros(B, D, device=dev())
+    before = x_adv.clone()
+    acc = torch.ones(B, device=dev())
+    lb = torch.full((B,), 5.0, device=dev())          # current loss (1.0) never beats the best
+    lbl, red = lb.clone(), torch.zeros(B, device=dev())  # no improvement since last check -> reduce
+    step = torch.full((B,), 0.1, device=dev())
+    ls = torch.zeros(4, B, device=dev())
+    flags = torch.zeros(3, B, dtype=torch.int32, device=dev())
+    done = torch.zeros(1, dtype=torch.int32, device=dev())
+    correct = torch.full((B,), 10, dtype=torch.int32, device=dev())
+    valid = torch.full((B,), HW, dtype=torch.int32, device=dev())
+    for _ in range(5):
+        x_best_adv.zero_()
+        x_adv.copy_(before)
+        acc.fill_(1.0), step.fill_(0.1), red.zero_()
+        mods.ops.apgd_bookkeep(correct, valid, torch.ones(B, device=dev()), acc, lb, lbl, red, step, ls, 3, 2, HW,
+                               False, flags, done)
+        assert flags[0].all() and not flags[1].any() and flags[2].all()
+        mods.ops.row_select([(x_best_adv, x_adv, flags[0], None), (x_best, x_adv, flags[1], None),
+                             (grad_best, grad, flags[1], None)], B, dev())
+        mods.ops.row_select([(x_adv, x_best, flags[2], flags[1]), (grad, grad_best, flags[2], flags[1])], B, dev())
+        assert torch.equal(x_best_adv, before) and torch.equal(x_adv, x_best) and torch.equal(grad, grad_best)
+        assert torch.equal(step, torch.full((B,), 0.05, device=dev()))
+
+
 @pytest.mark.parametrize("C,skew", [(9, False), (21, True), (151, False), (230, True)])
 def test_pixel_hist_vs_oracle(mods, C, skew):
     g = torch.Generator().manual_seed(C)
