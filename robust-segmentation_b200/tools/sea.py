@@ -27,12 +27,16 @@ LOSSES = ("mask-ce-bal", "mask-ce-avg", "js-avg")
 
 
 def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, losses=LOSSES,
-            n_batches=-1, device="cuda", keep_adv=False, group=None):
+            n_batches=-1, device="cuda", keep_adv=False, group=None, shard=True, seed=None):
     """Returns a dict: ``clean`` and per-loss ``{mAcc,aAcc,mIoU}``, ``worst_Acc``,
-    ``worst_Acc_indiv`` [A], ``final_miou``, ``n_images`` (+ ``x_adv`` per loss if keep_adv)."""
+    ``worst_Acc_indiv`` [A], ``final_miou``, ``n_images`` (+ ``x_adv`` per loss if keep_adv).
+
+    ``seed``: re-seed torch's generator with ``seed + batch_index`` before each batch, which makes
+    the random starts -- and therefore every counter -- independent of how the batches are sharded
+    over ranks.  ``shard=False`` ignores an initialised process group."""
     model.eval()
     dev = torch.device(device)
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    world = dist.get_world_size(group) if shard and dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     batches = []
     for i, vals in enumerate(loader):
@@ -47,7 +51,9 @@ def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, los
     per_loss = [[] for _ in range(A)]   # per batch [3, B, C] counters for every attack
     clean_cnt = []
     advs = [[] for _ in range(A)]
-    for x, y in batches[lo_b:hi_b]:
+    for bi, (x, y) in enumerate(batches[lo_b:hi_b], start=lo_b):
+        if seed is not None:
+            torch.manual_seed(seed + bi)
         x = x.to(dev, non_blocking=True)
         y = y.to(dev, non_blocking=True)
         with torch.no_grad():
@@ -69,7 +75,10 @@ def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, los
     zero = torch.zeros((3, 0, n_cls), dtype=torch.int64, device=dev)
     local = torch.stack([torch.cat(pl, 1) if pl else zero for pl in per_loss] +
                         [torch.cat(clean_cnt, 1) if clean_cnt else zero], 1)   # [3, A+1, n_local, C]
-    inter, tgt, prd, _ = rdist.allreduce_counters(n_total, img_lo, local[0], local[1], local[2], group=group)
+    if world > 1:
+        inter, tgt, prd, _ = rdist.allreduce_counters(n_total, img_lo, local[0], local[1], local[2], group=group)
+    else:
+        inter, tgt, prd = local[0], local[1], local[2]
     res = {"n_images": n_total, "clean": _finalize(inter[A].sum(0), tgt[A].sum(0), prd[A].sum(0))}
     for a, loss in enumerate(losses):
         res[loss] = _finalize(inter[a].sum(0), tgt[a].sum(0), prd[a].sum(0))
