@@ -565,8 +565,24 @@ def run_reference(args):
     }), flush=True)
 
 
+def _protect_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the driver wants ONE JSON line there.  Point
+    fd 1 at stderr for the run and hand back a file object on the real stdout for the JSON line."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
     a = parse()
+    _real_stdout = _protect_stdout()
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001  (only the final JSON lines go through print(..., flush=True))
+        if kw.get("file") is None:
+            kw["file"] = _real_stdout
+        _print(*args, **kw)
     if a.debug_stack:
         import faulthandler
 

@@ -13,7 +13,9 @@ dist.init_process_group("nccl", device_id=dev)
 torch.backends.cudnn.deterministic = True
 C = 21
 torch.manual_seed(0)
-model = cons.upernet_convnext("T", C, fast_upsample=True).to(dev).eval()
+# conv-only consumer: deterministic under cudnn.deterministic (UperNet's internal ATen bilinear
+# backward scatters with atomics, so its attack trajectories differ from run to run)
+model = cons.TinySegNet(C, hidden=16, seed=5).to(dev).eval()
 g = torch.Generator().manual_seed(3)
 loader = []
 for _ in range(4):
