@@ -21,7 +21,6 @@ Out of scope: L2 / L1 norms, DLR / margin losses, apgd_res
 pgd_filters -- never reached from tools/infer.py (norm is hard-set to "Linf" at
 tools/infer.py:327).  They raise NotImplementedError here.
 """
-import math
 from functools import partial
 
 import torch
@@ -357,5 +356,3 @@ def L1_projection(*args, **kwargs):
 def pgd_filters(*args, **kwargs):
     raise NotImplementedError("pgd_filters is outside the accelerated path")
 
-
-_ = math  # parity with the reference's import surface
