@@ -246,34 +246,53 @@ constexpr int kBwdOwned = 30;
 __global__ void __launch_bounds__(256)
     upsample_bwd_x4_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
                            int w, int strip) {
+  extern __shared__ float ky_tab[];  // [block rows of the strip + halo][4][3] y-weights
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = gw * kBwdOwned + lane - 1;  // lane 0 / 31: halo columns
-  if (gw * kBwdOwned >= w) return;          // whole warp past the image
   const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
-  const int W = 4 * w, H = 4 * h;
+  const int a_first = max(a0 - 1, 0), a_last = min(a1, h - 1);
+  // the y-weights depend only on the block row: build them once per block (ncu showed the first
+  // version spending most of its issue slots recomputing them per plane and row)
+  for (int i = threadIdx.x; i < (a_last - a_first + 1) * 4; i += blockDim.x) {
+    const int a = a_first + i / 4, r = i % 4;
+    const Tap t = make_tap(4 * a + r, 0.25f, h);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cell = a - 1 + c;
+      ky_tab[i * 3 + c] = (t.i0 == cell ? t.w0 : 0.f) + (t.i1 == cell ? t.w1 : 0.f);
+    }
+  }
+  __syncthreads();
+  if (gw * kBwdOwned >= w) return;  // whole warp past the image
+  const int W4 = w;                 // float4 per output row (W = 4w)
   const bool loads = b >= 0 && b < w;
   const bool owns = loads && lane >= 1 && lane <= kBwdOwned;
   const W3 kx = make_w3(min(max(b, 0), w - 1), 0.25f, w);  // transposed taps of my float4
+  const int bcl = min(max(b, 0), w - 1);
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
-    const float* src = gout + p * (int64_t)H * W + 4 * (int64_t)max(b, 0);
+    const float4* rowp = reinterpret_cast<const float4*>(gout) + (p * 4 * h + 4 * (int64_t)a_first) * W4 + bcl;
+    float* outp = gin + (p * h + (a_first - 1)) * (int64_t)w + bcl;  // cell row a-1 of the first block row
     float acc_prev = 0.f, acc_cur = 0.f, acc_next = 0.f;  // cells a-1, a, a+1 of the current block row
-    const int a_first = max(a0 - 1, 0), a_last = min(a1, h - 1);
     float4 v[4], nxt[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (loads) nxt[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(4 * a_first + i) * W));
+      if (loads) nxt[i] = __ldcs(rowp + (int64_t)i * W4);
     }
-    for (int a = a_first; a <= a_last; ++a) {
-      const W3 ky = make_w3(a, 0.25f, h);
+    const float* kyp = ky_tab;
+    for (int a = a_first; a <= a_last; ++a, kyp += 12, outp += w) {
+      rowp += 4 * (int64_t)W4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = nxt[i];
-      if (a < a_last) {  // prefetch the next block row while this one is reduced
+      if (a < a_last && loads) {  // prefetch the next block row while this one is reduced
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (loads) nxt[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(4 * (a + 1) + i) * W));
+        for (int i = 0; i < 4; ++i) nxt[i] = __ldcs(rowp + (int64_t)i * W4);
       }
+      const float4 k0 = *reinterpret_cast<const float4*>(kyp);      // rows 0,1 (+ first of row 1...)
+      const float4 k1 = *reinterpret_cast<const float4*>(kyp + 4);
+      const float4 k2 = *reinterpret_cast<const float4*>(kyp + 8);
+      const float ky[4][3] = {{k0.x, k0.y, k0.z}, {k0.w, k1.x, k1.y}, {k1.z, k1.w, k2.x}, {k2.y, k2.z, k2.w}};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // partial sums of this float4 for cells b-1, b, b+1
@@ -283,12 +302,12 @@ __global__ void __launch_bounds__(256)
         const float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's share for my cell
         const float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's share for my cell
         const float xr = (from_left + pc) + from_right;
-        acc_prev = fmaf(ky.k[i][0], xr, acc_prev);
-        acc_cur = fmaf(ky.k[i][1], xr, acc_cur);
-        acc_next = fmaf(ky.k[i][2], xr, acc_next);
+        acc_prev = fmaf(ky[i][0], xr, acc_prev);
+        acc_cur = fmaf(ky[i][1], xr, acc_cur);
+        acc_next = fmaf(ky[i][2], xr, acc_next);
       }
       // cell row a-1 has now received everything (block rows a-2 .. a)
-      if (owns && a - 1 >= a0 && a - 1 < a1) gin[(p * h + (a - 1)) * (int64_t)w + b] = acc_prev;
+      if (owns && a - 1 >= a0 && a - 1 < a1) *outp = acc_prev;
       acc_prev = acc_cur, acc_cur = acc_next, acc_next = 0.f;
     }
     // the last cell row of the strip when the strip ends at the image border
@@ -337,14 +356,15 @@ extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, i
     const int warps_x = (w + kBwdOwned - 1) / kBwdOwned;  // warps needed side by side
     const int wpb = warps_x < 8 ? warps_x : 8;            // warps per block (exact cover when <= 8)
     const int gx4 = (warps_x + wpb - 1) / wpb;
-    int strip = 32;  // cell rows per thread strip: 2 halo block rows per strip (6 % extra reads)
+    int strip = h >= 128 ? 64 : 32;  // cell rows per thread strip: 2 halo block rows per strip
     if (strip > h) strip = h;
     const int gy4 = (h + strip - 1) / strip;
     int64_t gz4 = ((int64_t)sm_count() * 16 + (int64_t)gx4 * gy4 - 1) / ((int64_t)gx4 * gy4);
     gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
     if (gz4 > 65535) gz4 = 65535;
-    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 32 * wpb, 0, stream>>>(gout, gin, planes, h,
-                                                                                  w, strip);
+    const size_t ky_bytes = (size_t)(strip + 2) * 12 * sizeof(float);
+    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 32 * wpb, ky_bytes, stream>>>(gout, gin, planes,
+                                                                                         h, w, strip);
     ROBSEG_LAUNCH_CHECK();
     return 0;
   }
