@@ -53,7 +53,9 @@ def parse():
                     help="re-forward every adversarial batch for its argmax map like tools/infer.py "
                          "(default: the attack returns it, SURVEY 8f-2)")
     ap.add_argument("--stock-upsample", action="store_true",
-                    help="keep F.interpolate for the consumer's final logit up-sampling (default: robseg kernels)")
+                    help="keep F.interpolate for every bilinear up-sampling of the consumer (default: robseg kernels)")
+    ap.add_argument("--logit-upsample-only", action="store_true",
+                    help="robseg kernels for the final logit up-sampling only, F.interpolate inside the decode head")
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
     return ap.parse_args()
 
@@ -187,7 +189,7 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = mods["consumers"].upernet_convnext(args.variant, args.classes,
-                                               fast_upsample=not args.stock_upsample).to(dev).eval()
+                                               fast_upsample=upsample_mode(args)).to(dev).eval()
     for p in model.parameters():
         p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
     B, C, S = args.batch, args.classes, args.size
@@ -272,8 +274,11 @@ def run_ours(args):
             "adversarial_argmax": "re-forward of x_adv (tools/infer.py:82-90)" if args.reforward else
             "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)",
             "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)",
-            "final_logit_upsample": "F.interpolate (stock)" if args.stock_upsample else
-            "robseg_upsample_bilinear_fwd/_bwd (SURVEY 8f-1; --stock-upsample restores F.interpolate)",
+            "bilinear_upsample": {False: "F.interpolate (stock) everywhere",
+                                  True: "robseg_upsample_bilinear_fwd/_bwd for the final logit up-sampling (SURVEY 8f-1)",
+                                  "all": "robseg_upsample_bilinear_fwd/_bwd for the final logit up-sampling (SURVEY 8f-1) "
+                                         "and the decode head's pyramid up-samplings; --stock-upsample restores F.interpolate"
+                                  }[upsample_mode(args)],
             "l2_note": "inputs larger than L2: logits/dlogits 2x%.2f GB per launch" % (B * C * S * S * 4 / 1e9),
             "parallelism": f"image-sharded dp{world}, one int64 all-reduce per step",
             "epilogue": "evalSEA greedy worst-case mIoU once per run outside the steps: %.1f ms (mIoU %.4f)" % (t_ep, miou),
@@ -316,6 +321,11 @@ def load_traffic(key):
 
 
 # ------------------------------------------------------------------------------ microbench
+def upsample_mode(args):
+    """consumers.UperNetConvNeXt.fast_upsample value for the command line."""
+    return False if args.stock_upsample else (True if args.logit_upsample_only else "all")
+
+
 def run_micro(args, mods, dev, rank, world):
     """BASELINE config 5: loss+dlogits, APGD step and histogram kernels alone at
     [micro_batch,150,512,512]; one JSON line with per-kernel GB/s vs the HBM roofline."""
@@ -335,13 +345,25 @@ def run_micro(args, mods, dev, rank, world):
     step = torch.full((B,), 16 / 255, device=dev)
     peaks = load_peaks()
     res = {}
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def time_it(name, fn, nbytes):
+    def time_it(name, fn, nbytes, inner=None):
+        """Median device time of fn().  inner: time only the events the wrapper records around
+        its own C call (ops.profile_start) -- for kernels shorter than the host-side work of a
+        call (output allocation, argument marshalling), which outer events would measure instead."""
         for _ in range(max(args.warmup, 3)):
             fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(max(args.steps, 5)):
+            if nbytes < 2 * l2_flush.numel():  # working set could stay in the 126 MB L2: evict it
+                l2_flush.zero_()
+            if inner:
+                ops.profile_start()
+                fn()
+                torch.cuda.synchronize()
+                ts.append(sum(ms for n, _, ms in ops.profile_stop() if n == inner))
+                continue
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
@@ -360,18 +382,21 @@ def run_micro(args, mods, dev, rank, world):
             z.numel() * es + 8 * y.numel())
     time_it("argmax", lambda: ops.loss_fwd_bwd(z, y, "argmax", want_grad=False, want_pred=True, want_stats=False),
             z.numel() * es + 16 * y.numel())
-    time_it("apgd_step", lambda: ops.apgd_step(x, xa, xo, gr, step, 8 / 255, 0.75, xn), 20 * x.numel())
+    time_it("apgd_step", lambda: ops.apgd_step(x, xa, xo, gr, step, 8 / 255, 0.75, xn), 20 * x.numel(), "apgd_step")
     pred = z.argmax(1)
-    time_it("pixel_hist/counts uniform-random", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel())
-    time_it("pixel_hist/full uniform-random", lambda: ops.pixel_hist(pred, y, C, want_hist=True, want_counts=False), 16 * y.numel())
+    time_it("pixel_hist/counts uniform-random", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel(), "pixel_hist")
+    time_it("pixel_hist/full uniform-random", lambda: ops.pixel_hist(pred, y, C, want_hist=True, want_counts=False), 16 * y.numel(),
+            "pixel_hist")
     ys = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.8, torch.full_like(y, 3), y)  # 80 % one class
     ps = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.7, ys, pred)
-    time_it("pixel_hist/counts skewed-80pct", lambda: ops.pixel_hist(ps, ys, C), 16 * y.numel())
+    time_it("pixel_hist/counts skewed-80pct", lambda: ops.pixel_hist(ps, ys, C), 16 * y.numel(), "pixel_hist")
     blk = torch.randint(0, C, (B, S // 64, S // 64), device=dev, generator=g)  # 64x64 constant regions
     yc = blk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()
     pblk = torch.where(torch.rand(blk.shape, device=dev, generator=g) < 0.7, blk, torch.randint_like(blk, C))
     pc = pblk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()  # region-wise right / wrong
-    time_it("pixel_hist/counts piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel())
+    time_it("pixel_hist/counts piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel(), "pixel_hist")
+    time_it("pixel_hist/full piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C, want_hist=True, want_counts=False),
+            16 * y.numel(), "pixel_hist")
     if args.micro_dtype == "fp32":
         import torch.nn.functional as F
 

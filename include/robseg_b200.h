@@ -194,8 +194,9 @@ int robseg_sea_worst_acc(const int64_t* inter, const int64_t* tgt, int A, int N,
  * Bilinear up-sampling, align_corners=False, of [planes, h, w] fp32 to [planes, H, W] and its
  * adjoint (planes = B*C).  Replaces the consumer's final logit up-sampling
  * nn.functional.interpolate(logits, size=input.shape[2:], mode="bilinear", align_corners=False)
- * (semseg/models/uperforseg.py:416-418, semseg/models/segmenter.py:228) and its autograd
- * backward -- SURVEY.md section 8f rank 1.  Index/weight arithmetic as ATen's
+ * (semseg/models/uperforseg.py:416-418, semseg/models/segmenter.py:228), the same call inside
+ * its decode head (uperforseg.py:193-198,282-303) and their autograd backward -- SURVEY.md
+ * section 8f rank 1.  Exact ratios 2, 4 and 8 have streaming specialisations.  Index/weight arithmetic as ATen's
  * area_pixel_compute_source_index.  The backward is a deterministic gather (no atomics):
  * gin[p,y,x] = sum over the output pixels whose taps include (y,x) of weight * gout.
  */
@@ -203,6 +204,16 @@ int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int h, int w, 
                                  int W, robseg_stream_t stream);
 int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W, float* gin, int h,
                                  int w, robseg_stream_t stream);
+/*
+ * Same adjoint for a gradient that is a [N, C, H, W] VIEW with contiguous rows: plane (n, c)
+ * starts at gout + n*batch_stride + c*chan_stride (elements).  The feature-pyramid
+ * up-samplings of the decode head (semseg/models/uperforseg.py:282-303) feed torch.cat, so
+ * their gradients arrive as channel slices of the concatenated gradient; this reads them in
+ * place instead of through a .contiguous() copy.  gin is contiguous [N*C, h, w].
+ */
+int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N, int C, int64_t batch_stride,
+                                         int64_t chan_stride, int H, int W, float* gin, int h, int w,
+                                         robseg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "robseg_sea_worst_acc": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "robseg_upsample_bilinear_fwd": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p]),
     "robseg_upsample_bilinear_bwd": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p]),
+    "robseg_upsample_bilinear_bwd_strided": (_i, [_p, _i64, _i, _i64, _i64, _i, _i, _p, _i, _i, _p]),
 }
 
 _lib = None

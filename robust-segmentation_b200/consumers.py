@@ -80,23 +80,28 @@ class UperHead(nn.Module):
         self.fuse = conv_bn_relu(len(w) * ch, ch, 3)
         self.classifier = nn.Conv2d(ch, n_cls, 1)
 
-    def forward(self, feats):
+    def forward(self, feats, interp=None):
+        def up(t, size):
+            if interp is not None and t.is_cuda and t.dtype == torch.float32:
+                return interp(t, size)
+            return F.interpolate(t, size=size, mode="bilinear", align_corners=False)
+
         top = feats[-1]
         size = top.shape[2:]
-        pooled = [top] + [F.interpolate(p(top), size=size, mode="bilinear", align_corners=False) for p in self.psp]
+        pooled = [top] + [up(p(top), size) for p in self.psp]
         lat = [l(f) for l, f in zip(self.lateral, feats)] + [self.bottleneck(torch.cat(pooled, 1))]
         for i in range(len(lat) - 1, 0, -1):
-            lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="bilinear",
-                                                    align_corners=False)
+            lat[i - 1] = lat[i - 1] + up(lat[i], lat[i - 1].shape[2:])
         outs = [f(l) for f, l in zip(self.fpn, lat)] + [lat[-1]]
         size0 = outs[0].shape[2:]
-        outs = [outs[0]] + [F.interpolate(o, size=size0, mode="bilinear", align_corners=False) for o in outs[1:]]
+        outs = [outs[0]] + [up(o, size0) for o in outs[1:]]
         return self.classifier(self.fuse(torch.cat(outs, 1)))
 
 
 class UperNetConvNeXt(nn.Module):
     """``fast_upsample=True`` routes the final logit up-sampling (the only [B,C,H,W]-sized op of
-    the model) through robseg's kernels instead of ``F.interpolate``."""
+    the model) through robseg's kernels instead of ``F.interpolate`` (SURVEY.md 8f rank 1);
+    ``fast_upsample="all"`` also routes the bilinear up-samplings inside the decode head."""
 
     def __init__(self, variant="T", n_cls=150, fast_upsample=False):
         super().__init__()
@@ -107,10 +112,11 @@ class UperNetConvNeXt(nn.Module):
 
     def forward(self, x, lbl=None):
         feats = self.backbone(x)
-        low = self.decode_head(feats)
-        if self.fast_upsample and low.is_cuda and low.dtype == torch.float32:
+        fast = self.fast_upsample and x.is_cuda
+        if fast:
             from . import ops
-
+        low = self.decode_head(feats, ops.upsample_bilinear if fast and self.fast_upsample == "all" else None)
+        if fast and low.dtype == torch.float32:
             logits = ops.upsample_bilinear(low, x.shape[2:])
         else:
             logits = F.interpolate(low, size=x.shape[2:], mode="bilinear", align_corners=False)

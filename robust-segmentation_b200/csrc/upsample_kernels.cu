@@ -31,16 +31,18 @@ __device__ __forceinline__ Tap make_tap(int dst, float scale, int in_size) {
   return t;
 }
 
-// out[p, Y, X..X+3]; grid (ceil(W/4/128), H, plane groups), block 128.  The taps depend only on
-// (Y, X), so a block computes them once and then streams over its planes.  For up-sampling
+// out[p, Y, X..X+3]; grid (ceil(H*ceil(W/4)/128), 1, plane groups), block 128: a thread owns one
+// quad of the flattened plane (narrow planes still fill their blocks).  The taps depend only on
+// (Y, X), so a thread computes them once and then streams over its planes.  For up-sampling
 // ratios >= 2 the four outputs of a thread read at most three adjacent input columns: 6 loads
 // per 16-byte store instead of 16.
 __global__ void __launch_bounds__(128)
     upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h,
                         int w, int H, int W, float sy, float sx) {
-  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int Y = blockIdx.y;
-  if (X0 >= W) return;
+  const int quads = (W + 3) / 4;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * quads) return;
+  const int Y = t / quads, X0 = (t - Y * quads) * 4;
   const Tap ty = make_tap(Y, sy, h);
   Tap tx[4];
 #pragma unroll
@@ -92,9 +94,9 @@ __global__ void __launch_bounds__(128)
 // reduce along x, reduce along y, write each input cell exactly once.
 // Shared layout: region [RY][RXP] | xred [TX][RYP] | wx [TX][KX] | wy [TY][KY] | xs [TX] | ys [TY]
 __global__ void __launch_bounds__(256)
-    upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
-                        int w, int H, int W, float sy, float sx, int TY, int TX, int RY, int RX, int KY,
-                        int KX) {
+    upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int C,
+                        int64_t bs, int64_t cs, int h, int w, int H, int W, float sy, float sx, int TY,
+                        int TX, int RY, int RX, int KY, int KX) {
   extern __shared__ float shm[];
   const int RXP = RX | 1, RYP = RY | 1;  // odd strides: conflict-free column walks
   float* region = shm;
@@ -130,10 +132,11 @@ __global__ void __launch_bounds__(256)
     }
     (isx ? xs[i] : ys[i - TX]) = a - (isx ? X0 : Y0);
   }
-  const bool vec = (W % 4 == 0) && (RX % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) % 16 == 0);
+  const bool vec = (W % 4 == 0) && (RX % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) % 16 == 0) &&
+                   bs % 4 == 0 && cs % 4 == 0;
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
     __syncthreads();  // tables ready / previous plane's xred consumed
-    const float* src = gout + p * (int64_t)H * W;
+    const float* src = gout + (p / C) * bs + (p % C) * cs;
     // ---- stage the region (zero beyond the image) --------------------------------------------
     if (vec) {
       const int nx4 = RX / 4;
@@ -177,19 +180,22 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- exact x4 specialisations (H == 4h, W == 4w: UperNet's logits) ----------------------------
-// Output block (4 rows x 4 cols) <-> input cell (a, b): its taps only touch cells a-1..a+1 x
-// b-1..b+1.  Dense 3-tap weight rows (zeros included, image borders folded in through
-// make_tap) make both directions branch-free.
-struct W3 {
-  float k[4][3];  // k[j][c]: weight of input (base-1+c) for output 4*base+j
+// ---- exact power-of-two specialisations (H == R*h, W == R*w, R = 2, 4, 8, 16) -------------------
+// x4 is UperNet's final logit up-sampling; x2 / x4 / x8 are the feature-pyramid up-samplings of
+// its decode head (semseg/models/uperforseg.py:282-303); x16 is Segmenter's (segmenter.py:228).  Output block (R rows x R cols) <-> input
+// cell (a, b): its taps only touch cells a-1..a+1 x b-1..b+1.  Dense 3-tap weight rows (zeros
+// included, image borders folded in through make_tap) make both directions branch-free.
+template <int R>
+struct WR {
+  float k[R][3];  // k[j][c]: weight of input (base-1+c) for output R*base+j
 };
 
-__device__ __forceinline__ W3 make_w3(int base, float scale, int in_size) {
-  W3 r;
+template <int R>
+__device__ __forceinline__ WR<R> make_wr(int base, int in_size) {
+  WR<R> r;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const Tap t = make_tap(4 * base + j, scale, in_size);
+  for (int j = 0; j < R; ++j) {
+    const Tap t = make_tap(R * base + j, 1.f / R, in_size);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int cell = base - 1 + c;
@@ -199,112 +205,152 @@ __device__ __forceinline__ W3 make_w3(int base, float scale, int in_size) {
   return r;
 }
 
-// grid (ceil(w/128), h, plane groups), block 128: thread = one input cell column b of cell row a,
-// produces the 4x4 output block from 9 loads (separable: 3 rows x 4 horizontal outputs, then
-// vertical), stores four coalesced float4 rows.
+// R adjacent floats, vector width min(R, 4); p is R*4-byte aligned (16 for R = 8)
+template <int R>
+__device__ __forceinline__ void store_row(float* p, const float (&v)[R]) {
+  if constexpr (R == 2) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else {
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q)
+      __stcs(reinterpret_cast<float4*>(p) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
+}
+template <int R>
+__device__ __forceinline__ void load_row(const float* p, float (&v)[R]) {
+  if constexpr (R == 2) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    v[0] = t.x, v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(p) + q);
+      v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+    }
+  }
+}
+
+// grid (ceil(h*w/128), 1, plane groups), block 128: thread = one input cell (a, b) of the
+// flattened plane (narrow planes still fill their blocks), produces the RxR output block from 9
+// loads (separable: 3 rows x R horizontal outputs, then vertical), stores R coalesced rows.
+template <int R>
 __global__ void __launch_bounds__(128)
-    upsample_fwd_x4_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h,
-                           int w) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const int a = blockIdx.y;
-  if (b >= w) return;
-  const int H = 4 * h, W = 4 * w;
-  const W3 kx = make_w3(b, 0.25f, w), ky = make_w3(a, 0.25f, h);
+    upsample_fwd_pow2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes,
+                             int h, int w) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= h * w) return;
+  const int a = cell / w, b = cell - a * w;
+  const int H = R * h, W = R * w;
+  const WR<R> kx = make_wr<R>(b, w), ky = make_wr<R>(a, h);
   const int cm = max(b - 1, 0), cp = min(b + 1, w - 1);
   const int rm = max(a - 1, 0), rp = min(a + 1, h - 1);
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
     const float* base = in + p * (int64_t)h * w;
-    float hx[3][4];
+    float hx[3][R];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float* row = base + (int64_t)(r == 0 ? rm : (r == 1 ? a : rp)) * w;
       const float v0 = __ldg(row + cm), v1 = __ldg(row + b), v2 = __ldg(row + cp);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hx[r][j] = kx.k[j][0] * v0 + kx.k[j][1] * v1 + kx.k[j][2] * v2;
+      for (int j = 0; j < R; ++j) hx[r][j] = kx.k[j][0] * v0 + kx.k[j][1] * v1 + kx.k[j][2] * v2;
     }
-    float* o = out + (p * H + 4 * a) * (int64_t)W + 4 * b;
+    float* o = out + (p * H + R * a) * (int64_t)W + R * b;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 v;
-      v.x = ky.k[i][0] * hx[0][0] + ky.k[i][1] * hx[1][0] + ky.k[i][2] * hx[2][0];
-      v.y = ky.k[i][0] * hx[0][1] + ky.k[i][1] * hx[1][1] + ky.k[i][2] * hx[2][1];
-      v.z = ky.k[i][0] * hx[0][2] + ky.k[i][1] * hx[1][2] + ky.k[i][2] * hx[2][2];
-      v.w = ky.k[i][0] * hx[0][3] + ky.k[i][1] * hx[1][3] + ky.k[i][2] * hx[2][3];
-      __stcs(reinterpret_cast<float4*>(o + (int64_t)i * W), v);
+    for (int i = 0; i < R; ++i) {
+      float v[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        v[j] = ky.k[i][0] * hx[0][j] + ky.k[i][1] * hx[1][j] + ky.k[i][2] * hx[2][j];
+      store_row<R>(o + (int64_t)i * W, v);
     }
   }
 }
 
-// grid (x groups, strips, plane groups), block = up to 8 warps side by side.  A warp covers 30
-// owned input cell columns plus one halo lane on each side (lane 0 and lane 31 only feed their
-// neighbours), so the x-reduction needs no cross-warp traffic and no special cases.  A lane walks
-// down the output rows of its strip of cell rows [a0, a1): one coalesced float4 per output row
-// straight from global memory, x-reduction in registers with two shuffles, y-reduction in three
-// rotating accumulators; each input cell is written once.  No shared memory, no atomics.
-constexpr int kBwdOwned = 30;
-
+// grid (x groups, strips, plane groups), block = up to 8 warps side by side.  A warp covers
+// `owned` (<= 30) input cell columns plus one halo lane on each side (the halo lanes only feed
+// their neighbours), so the x-reduction needs no cross-warp traffic and no special cases.  A lane
+// walks down the output rows of its strip of cell rows [a0, a1): R coalesced floats per output
+// row straight from global memory, G rows in flight while the previous G are reduced;
+// x-reduction in registers with two shuffles, y-reduction in three rotating accumulators; each
+// input cell is written once.  No atomics.  Plane p = (p / C, p % C) of a [N, C, H, W] view with
+// batch / channel strides bs / cs (elements): gradients of torch.cat slices are read in place.
+template <int R>
 __global__ void __launch_bounds__(256)
-    upsample_bwd_x4_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int h,
-                           int w, int strip) {
-  extern __shared__ float ky_tab[];  // [block rows of the strip + halo][4][3] y-weights
+    upsample_bwd_pow2_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes,
+                             int C, int64_t bs, int64_t cs, int h, int w, int strip, int owned) {
+  constexpr int G = R < 4 ? R : (R > 8 ? 2 : 4);  // output rows per prefetch group
+  constexpr int KYS = (3 * R + 3) & ~3;       // padded floats of y-weights per cell row
+  extern __shared__ __align__(16) float ky_tab[];  // [cell rows of the strip + halo][KYS]
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int b = gw * kBwdOwned + lane - 1;  // lane 0 / 31: halo columns
+  const int b = gw * owned + lane - 1;  // lane 0 / owned+1: halo columns
   const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
   const int a_first = max(a0 - 1, 0), a_last = min(a1, h - 1);
-  // the y-weights depend only on the block row: build them once per block (ncu showed the first
-  // version spending most of its issue slots recomputing them per plane and row)
-  for (int i = threadIdx.x; i < (a_last - a_first + 1) * 4; i += blockDim.x) {
-    const int a = a_first + i / 4, r = i % 4;
-    const Tap t = make_tap(4 * a + r, 0.25f, h);
+  // the y-weights depend only on the cell row: build them once per block
+  for (int i = threadIdx.x; i < (a_last - a_first + 1) * R; i += blockDim.x) {
+    const int a = a_first + i / R, r = i % R;
+    const Tap t = make_tap(R * a + r, 1.f / R, h);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int cell = a - 1 + c;
-      ky_tab[i * 3 + c] = (t.i0 == cell ? t.w0 : 0.f) + (t.i1 == cell ? t.w1 : 0.f);
+      ky_tab[(i / R) * KYS + r * 3 + c] = (t.i0 == cell ? t.w0 : 0.f) + (t.i1 == cell ? t.w1 : 0.f);
     }
   }
   __syncthreads();
-  if (gw * kBwdOwned >= w) return;  // whole warp past the image
-  const int W4 = w;                 // float4 per output row (W = 4w)
-  const bool loads = b >= 0 && b < w;
-  const bool owns = loads && lane >= 1 && lane <= kBwdOwned;
-  const W3 kx = make_w3(min(max(b, 0), w - 1), 0.25f, w);  // transposed taps of my float4
+  if (gw * owned >= w) return;  // whole warp past the image
+  const int64_t W = (int64_t)R * w;
+  const bool loads = b >= 0 && b < w && lane <= owned + 1;
+  const bool owns = loads && lane >= 1 && lane <= owned;
   const int bcl = min(max(b, 0), w - 1);
+  const WR<R> kx = make_wr<R>(bcl, w);  // transposed taps of my R outputs
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
-    const float4* rowp = reinterpret_cast<const float4*>(gout) + (p * 4 * h + 4 * (int64_t)a_first) * W4 + bcl;
+    const float* rowp = gout + (p / C) * bs + (p % C) * cs + (int64_t)R * a_first * W + R * bcl;
     float* outp = gin + (p * h + (a_first - 1)) * (int64_t)w + bcl;  // cell row a-1 of the first block row
     float acc_prev = 0.f, acc_cur = 0.f, acc_next = 0.f;  // cells a-1, a, a+1 of the current block row
-    float4 v[4], nxt[4];
+    float v[G][R], nxt[G][R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (loads) nxt[i] = __ldcs(rowp + (int64_t)i * W4);
+    for (int i = 0; i < G; ++i) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) nxt[i][j] = 0.f;
+      if (loads) load_row<R>(rowp + i * W, nxt[i]);
     }
     const float* kyp = ky_tab;
-    for (int a = a_first; a <= a_last; ++a, kyp += 12, outp += w) {
-      rowp += 4 * (int64_t)W4;
+    for (int a = a_first; a <= a_last; ++a, kyp += KYS, outp += w) {
+      float ky[KYS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = nxt[i];
-      if (a < a_last && loads) {  // prefetch the next block row while this one is reduced
-#pragma unroll
-        for (int i = 0; i < 4; ++i) nxt[i] = __ldcs(rowp + (int64_t)i * W4);
+      for (int q = 0; q < KYS / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(kyp + 4 * q);
+        ky[4 * q] = t.x, ky[4 * q + 1] = t.y, ky[4 * q + 2] = t.z, ky[4 * q + 3] = t.w;
       }
-      const float4 k0 = *reinterpret_cast<const float4*>(kyp);      // rows 0,1 (+ first of row 1...)
-      const float4 k1 = *reinterpret_cast<const float4*>(kyp + 4);
-      const float4 k2 = *reinterpret_cast<const float4*>(kyp + 8);
-      const float ky[4][3] = {{k0.x, k0.y, k0.z}, {k0.w, k1.x, k1.y}, {k1.z, k1.w, k2.x}, {k2.y, k2.z, k2.w}};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // partial sums of this float4 for cells b-1, b, b+1
-        const float pl = kx.k[0][0] * v[i].x + kx.k[1][0] * v[i].y + kx.k[2][0] * v[i].z + kx.k[3][0] * v[i].w;
-        const float pc = kx.k[0][1] * v[i].x + kx.k[1][1] * v[i].y + kx.k[2][1] * v[i].z + kx.k[3][1] * v[i].w;
-        const float pr = kx.k[0][2] * v[i].x + kx.k[1][2] * v[i].y + kx.k[2][2] * v[i].z + kx.k[3][2] * v[i].w;
-        const float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's share for my cell
-        const float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's share for my cell
-        const float xr = (from_left + pc) + from_right;
-        acc_prev = fmaf(ky[i][0], xr, acc_prev);
-        acc_cur = fmaf(ky[i][1], xr, acc_cur);
-        acc_next = fmaf(ky[i][2], xr, acc_next);
+      for (int g = 0; g < R / G; ++g) {
+        rowp += G * W;
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+          for (int j = 0; j < R; ++j) v[i][j] = nxt[i][j];
+        if ((g + 1 < R / G || a < a_last) && loads) {  // prefetch the next G rows while these are reduced
+#pragma unroll
+          for (int i = 0; i < G; ++i) load_row<R>(rowp + i * W, nxt[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          // partial sums of my R outputs for cells b-1, b, b+1
+          float pl = 0.f, pc = 0.f, pr = 0.f;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            pl = fmaf(kx.k[j][0], v[i][j], pl);
+            pc = fmaf(kx.k[j][1], v[i][j], pc);
+            pr = fmaf(kx.k[j][2], v[i][j], pr);
+          }
+          const float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's share for my cell
+          const float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's share for my cell
+          const float xr = (from_left + pc) + from_right;
+          const int r = g * G + i;
+          acc_prev = fmaf(ky[3 * r], xr, acc_prev);
+          acc_cur = fmaf(ky[3 * r + 1], xr, acc_cur);
+          acc_next = fmaf(ky[3 * r + 2], xr, acc_next);
+        }
       }
       // cell row a-1 has now received everything (block rows a-2 .. a)
       if (owns && a - 1 >= a0 && a - 1 < a1) *outp = acc_prev;
@@ -319,54 +365,87 @@ __global__ void __launch_bounds__(256)
 
 using namespace robseg;
 
+template <int R>
+static int launch_fwd_pow2(const float* in, float* out, int64_t planes, int h, int w, cudaStream_t stream) {
+  const int gx = (h * w + 127) / 128;
+  // ~32 resident blocks per SM worth of cell tiles; the rest of the parallelism is planes
+  int64_t gz = ((int64_t)sm_count() * 32 + gx - 1) / gx;
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  upsample_fwd_pow2_kernel<R><<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(in, out, planes, h, w);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int R>
+static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C, int64_t bs, int64_t cs,
+                           int h, int w, cudaStream_t stream) {
+  // cells per warp: spread the columns evenly over the fewest warps (<= 30 owned + 2 halo lanes)
+  const int warps_x = (w + 29) / 30;
+  const int owned = (w + warps_x - 1) / warps_x;
+  const int wpb = warps_x < 8 ? warps_x : 8;  // warps per block (exact cover when <= 8)
+  const int gx = (warps_x + wpb - 1) / wpb;
+  int strip = h >= 128 ? 64 : 32;  // cell rows per thread strip: 2 halo block rows per strip
+  if (strip > h) strip = h;
+  const int gy = (h + strip - 1) / strip;
+  int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  const size_t ky_bytes = (size_t)(strip + 2) * ((3 * R + 3) & ~3) * sizeof(float);
+  upsample_bwd_pow2_kernel<R><<<dim3(gx, gy, (unsigned)gz), 32 * wpb, ky_bytes, stream>>>(
+      gout, gin, planes, C, bs, cs, h, w, strip, owned);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int h, int w, float* out,
                                             int H, int W, robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ROBSEG_REQUIRE(in && out, "NULL pointer");
-  ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0 && H <= 65535, "bad shape");
+  ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-  if (H == 4 * h && W == 4 * w && reinterpret_cast<uintptr_t>(out) % 16 == 0 && h <= 65535) {
-    const int gx4 = (w + 127) / 128;
-    int64_t gz4 = ((int64_t)sm_count() * 32 + (int64_t)gx4 * h - 1) / ((int64_t)gx4 * h);
-    gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
-    if (gz4 > 65535) gz4 = 65535;
-    upsample_fwd_x4_kernel<<<dim3(gx4, h, (unsigned)gz4), 128, 0, stream>>>(in, out, planes, h, w);
-    ROBSEG_LAUNCH_CHECK();
-    return 0;
+  if (H % h == 0 && W % w == 0 && H / h == W / w && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+      (int64_t)h * w < ((int64_t)1 << 30)) {
+    switch (H / h) {
+      case 2: return launch_fwd_pow2<2>(in, out, planes, h, w, stream);
+      case 4: return launch_fwd_pow2<4>(in, out, planes, h, w, stream);
+      case 8: return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
+      default: break;
+    }
   }
-  const int gx = (W + 4 * 128 - 1) / (4 * 128);
-  // ~32 resident blocks per SM worth of (x, y) tiles; the rest of the parallelism is planes
-  int64_t gz = ((int64_t)sm_count() * 32 + (int64_t)gx * H - 1) / ((int64_t)gx * H);
+  const int64_t quads = (int64_t)H * ((W + 3) / 4);
+  ROBSEG_REQUIRE(quads < ((int64_t)1 << 30), "plane too large");
+  const int gx = (int)((quads + 127) / 128);
+  // ~32 resident blocks per SM worth of quads; the rest of the parallelism is planes
+  int64_t gz = ((int64_t)sm_count() * 32 + gx - 1) / gx;
   if (gz < 1) gz = 1;
   if (gz > planes) gz = planes;
   if (gz > 65535) gz = 65535;
-  dim3 grid((unsigned)gx, (unsigned)H, (unsigned)gz);
+  dim3 grid((unsigned)gx, 1, (unsigned)gz);
   upsample_fwd_kernel<<<grid, 128, 0, stream>>>(in, out, planes, h, w, H, W, sy, sx);
   ROBSEG_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W, float* gin,
-                                            int h, int w, robseg_stream_t stream_) {
+extern "C" int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N, int C,
+                                                    int64_t batch_stride, int64_t chan_stride, int H,
+                                                    int W, float* gin, int h, int w,
+                                                    robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ROBSEG_REQUIRE(gout && gin, "NULL pointer");
-  ROBSEG_REQUIRE(planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  ROBSEG_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  ROBSEG_REQUIRE(batch_stride >= 0 && chan_stride >= (int64_t)H * W, "planes overlap");
+  const int64_t planes = N * C, bs = batch_stride, cs = chan_stride;
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-  if (H == 4 * h && W == 4 * w && reinterpret_cast<uintptr_t>(gout) % 16 == 0) {
-    const int warps_x = (w + kBwdOwned - 1) / kBwdOwned;  // warps needed side by side
-    const int wpb = warps_x < 8 ? warps_x : 8;            // warps per block (exact cover when <= 8)
-    const int gx4 = (warps_x + wpb - 1) / wpb;
-    int strip = h >= 128 ? 64 : 32;  // cell rows per thread strip: 2 halo block rows per strip
-    if (strip > h) strip = h;
-    const int gy4 = (h + strip - 1) / strip;
-    int64_t gz4 = ((int64_t)sm_count() * 16 + (int64_t)gx4 * gy4 - 1) / ((int64_t)gx4 * gy4);
-    gz4 = gz4 < 1 ? 1 : (gz4 > planes ? planes : gz4);
-    if (gz4 > 65535) gz4 = 65535;
-    const size_t ky_bytes = (size_t)(strip + 2) * 12 * sizeof(float);
-    upsample_bwd_x4_kernel<<<dim3(gx4, gy4, (unsigned)gz4), 32 * wpb, ky_bytes, stream>>>(gout, gin, planes,
-                                                                                         h, w, strip);
-    ROBSEG_LAUNCH_CHECK();
-    return 0;
+  if (H % h == 0 && W % w == 0 && H / h == W / w && reinterpret_cast<uintptr_t>(gout) % 16 == 0 &&
+      bs % 4 == 0 && cs % 4 == 0) {
+    switch (H / h) {
+      case 2: return launch_bwd_pow2<2>(gout, gin, planes, C, bs, cs, h, w, stream);
+      case 4: return launch_bwd_pow2<4>(gout, gin, planes, C, bs, cs, h, w, stream);
+      case 8: return launch_bwd_pow2<8>(gout, gin, planes, C, bs, cs, h, w, stream);
+      case 16: return launch_bwd_pow2<16>(gout, gin, planes, C, bs, cs, h, w, stream);
+      default: break;
+    }
   }
   // tile of input cells per CTA: shrink until the staged output region fits ~48 KB
   int TY = 8, TX = 32;
@@ -392,8 +471,15 @@ extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, i
   if (gz > planes) gz = planes;
   if (gz > 65535) gz = 65535;
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
-  upsample_bwd_kernel<<<grid, 256, smem, stream>>>(gout, gin, planes, h, w, H, W, sy, sx, TY, TX, RY, RX,
-                                                   KY, KX);
+  upsample_bwd_kernel<<<grid, 256, smem, stream>>>(gout, gin, planes, C, bs, cs, h, w, H, W, sy, sx, TY,
+                                                   TX, RY, RX, KY, KX);
   ROBSEG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W, float* gin,
+                                            int h, int w, robseg_stream_t stream_) {
+  ROBSEG_REQUIRE(planes > 0 && planes <= 0x7fffffff && H > 0 && W > 0, "bad shape");
+  return robseg_upsample_bilinear_bwd_strided(gout, 1, (int)planes, 0, (int64_t)H * W, H, W, gin, h, w,
+                                              stream_);
 }

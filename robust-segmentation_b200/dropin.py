@@ -37,13 +37,19 @@ def install(reference_root=None):
     return attacker
 
 
-def fast_logit_upsample(model):
+def fast_logit_upsample(model, head=False):
     """Route the final logit up-sampling of a reference model through robseg's kernels.
 
     Works for models shaped like the reference's ``UperNetForSemanticSegmentation``
     (semseg/models/uperforseg.py:382-439: ``backbone`` -> ``decode_head`` -> bilinear
     up-sampling to the input size).  Only the eval-mode forward the attack uses is replaced;
-    the training forward (loss + aux head) is left alone."""
+    the training forward (loss + aux head) is left alone.
+
+    ``head=True`` also routes the bilinear up-samplings inside the decode head (PSP, top-down
+    path, pyramid fusion: uperforseg.py:193-198,282-303), which call
+    ``nn.functional.interpolate`` by name: that name is rebound to ``ops.interpolate`` for the
+    duration of the head's forward only (other modes / dtypes / devices fall through to the
+    stock function)."""
     import types
 
     from . import ops
@@ -55,7 +61,12 @@ def fast_logit_upsample(model):
     def forward(self, input=None, lbl=None):
         if lbl is not None or self.training or not input.is_cuda:
             return stock_forward(input, lbl)
-        low = self.decode_head(self.backbone(input))
+        feats = self.backbone(input)
+        if head:
+            with ops.patched_interpolate():
+                low = self.decode_head(feats)
+        else:
+            low = self.decode_head(feats)
         return ops.upsample_bilinear(low.float(), input.shape[2:])
 
     model.forward = types.MethodType(forward, model)

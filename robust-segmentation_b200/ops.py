@@ -315,14 +315,17 @@ def _upsample_fwd(x, H, W):
 def _upsample_bwd(g, h, w):
     _need_cuda(g)
     lib = _lib.load()
-    g = g.contiguous()
     if g.dtype != torch.float32:
         g = g.float()
     B, Cn, H, W = g.shape
+    # a channel slice of a torch.cat gradient (rows contiguous, planes strided) is read in place
+    if not (g.stride(3) == 1 and g.stride(2) == W and g.stride(1) >= H * W and g.stride(0) >= 0):
+        g = g.contiguous()
     gin = torch.empty((B, Cn, h, w), dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device), _timed("upsample_bwd", 4 * (g.numel() + gin.numel())):
-        rc = lib.robseg_upsample_bilinear_bwd(g.data_ptr(), B * Cn, H, W, gin.data_ptr(), h, w, _stream())
-    _lib.check(rc, "robseg_upsample_bilinear_bwd")
+        rc = lib.robseg_upsample_bilinear_bwd_strided(g.data_ptr(), B, Cn, g.stride(0), g.stride(1), H, W,
+                                                      gin.data_ptr(), h, w, _stream())
+    _lib.check(rc, "robseg_upsample_bilinear_bwd_strided")
     _lib.count(1)
     return gin
 
@@ -344,6 +347,33 @@ def upsample_bilinear(x, size):
     gather backward.  SURVEY.md section 8f rank 1."""
     H, W = (size, size) if isinstance(size, int) else (int(size[0]), int(size[1]))
     return _UpsampleBilinear.apply(x, H, W)
+
+
+_stock_interpolate = torch.nn.functional.interpolate
+
+
+def interpolate(input, size=None, scale_factor=None, mode="nearest", align_corners=None, **kw):
+    """``torch.nn.functional.interpolate`` with the bilinear / align_corners=False / fp32 / CUDA /
+    4-D case routed to :func:`upsample_bilinear`; every other call goes to the stock function."""
+    if (mode == "bilinear" and not align_corners and size is not None and scale_factor is None and not kw
+            and input.is_cuda and input.dim() == 4 and input.dtype == torch.float32):
+        return upsample_bilinear(input, size)
+    return _stock_interpolate(input, size=size, scale_factor=scale_factor, mode=mode,
+                              align_corners=align_corners, **kw)
+
+
+class patched_interpolate:
+    """Context manager: ``torch.nn.functional.interpolate`` -> :func:`interpolate` while a model
+    that calls it by that name (the reference's UperNet head, semseg/models/uperforseg.py:193,
+    282,297) runs its forward.  Restores the stock function on exit."""
+
+    def __enter__(self):
+        self.prev = torch.nn.functional.interpolate
+        torch.nn.functional.interpolate = interpolate
+        return self
+
+    def __exit__(self, *a):
+        torch.nn.functional.interpolate = self.prev
 
 
 # ----------------------------------------------------------------------------------------------

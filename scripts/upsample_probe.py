@@ -1,19 +1,48 @@
-"""Time / profile the x4 up-sampling kernels on the config-2 logits shape."""
-import sys, torch
+"""Time robseg's bilinear up-sampling kernels against ATen on the decode-head and logit shapes.
+  python scripts/upsample_probe.py"""
+import importlib
+import statistics
+import sys
+
+import torch
+import torch.nn.functional as F
+
 sys.path.insert(0, ".")
-import __graft_entry__ as ge
-ge.load_package()
-from importlib import import_module
-ops = import_module("robseg_b200.ops")
+ops = importlib.import_module("robust-segmentation_b200.ops")
 dev = torch.device("cuda:0")
-B, C, S = 16, 150, 512
 g = torch.Generator(device=dev).manual_seed(0)
-low = torch.randn(B, C, S // 4, S // 4, device=dev, generator=g)
-gup = torch.randn(B, C, S, S, device=dev, generator=g)
-for name, fn in (("fwd", lambda: ops._upsample_fwd(low, S, S)), ("bwd", lambda: ops._upsample_bwd(gup, S // 4, S // 4))):
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def t(fn, inner):
+    for _ in range(2):
+        fn()
     ts = []
-    for _ in range(6):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
-    ms = sorted(ts)[3]
-    print(name, f"{ms:.3f} ms", f"{4 * (low.numel() + gup.numel()) / ms / 1e6:.0f} GB/s", flush=True)
+    for _ in range(5):
+        flush.zero_()
+        if inner:
+            ops.profile_start()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(sum(ms for n, _, ms in ops.profile_stop() if n == inner))
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+shapes = [(16, 150, 128, 512), (16, 512, 64, 128), (16, 512, 32, 128), (16, 512, 16, 128), (16, 512, 32, 64),
+          (16, 512, 16, 32), (16, 512, 6, 16), (16, 512, 1, 16), (2, 150, 32, 512)]
+for B, C, s, S in shapes:
+    low = torch.randn(B, C, s, s, device=dev, generator=g)
+    gup = torch.randn(B, C, S, S, device=dev, generator=g)
+    nb = 4 * (low.numel() + gup.numel())
+    lr = low.clone().requires_grad_()
+    up = F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False)
+    r = [t(lambda: ops._upsample_fwd(low, S, S), "upsample_fwd"), t(lambda: ops._upsample_bwd(gup, s, s), "upsample_bwd"),
+         t(lambda: F.interpolate(low, size=(S, S), mode="bilinear", align_corners=False), None),
+         t(lambda: torch.autograd.grad(up, [lr], grad_outputs=gup, retain_graph=True), None)]
+    print(f"[{B},{C},{s},{s}]->{S}: " + "  ".join(f"{n} {ms*1e3:7.1f} us {nb/ms/1e6:6.0f} GB/s" for n, ms in
+                                                   zip(("fwd", "bwd", "aten_fwd", "aten_bwd"), r)), flush=True)
+    del up, lr, low, gup

@@ -327,6 +327,28 @@ def test_pixel_hist_vs_oracle(mods, C, skew):
         assert np.array_equal(out2[k].cpu().numpy(), ref[k]), k
 
 
+@pytest.mark.parametrize("n,C", [(64, 150), (5, 151)])
+def test_pixel_hist_config5_size(mods, n, C):
+    """BASELINE config-5 size (64 x 512 x 512): blocks cross image boundaries and the byte
+    counters of the atomic-free kernel are folded several times per block."""
+    g = torch.Generator(device=dev()).manual_seed(n)
+    H = W = 512 if n == 64 else 509  # odd HW: every other image starts 8-byte aligned only
+    blk = torch.randint(0, C, (n, (H + 31) // 32, (W + 31) // 32), device=dev(), generator=g)
+    tgt = blk.repeat_interleave(32, 1).repeat_interleave(32, 2)[:, :H, :W].contiguous()
+    tgt[:, ::3] = torch.randint(0, C, tgt[:, ::3].shape, device=dev(), generator=g)  # coherent + random rows
+    pred = torch.where(torch.rand(n, H, W, device=dev(), generator=g) < 0.6, tgt,
+                       torch.randint(0, C, (n, H, W), device=dev(), generator=g))
+    tgt = torch.where(torch.rand(n, H, W, device=dev(), generator=g) < 0.05, torch.full_like(tgt, -1), tgt)
+    ref = O.pixel_hist(pred.cpu().numpy(), tgt.cpu().numpy(), C)
+    full = mods.ops.pixel_hist(pred, tgt, C, want_hist=True)
+    cnt = mods.ops.pixel_hist(pred, tgt, C)
+    assert np.array_equal(full["hist"].cpu().numpy(), ref["hist"])
+    for k in ("inter", "tgt", "prd"):
+        assert np.array_equal(full[k].cpu().numpy(), ref[k]), k
+        assert np.array_equal(cnt[k].cpu().numpy(), ref[k]), k
+    assert int(cnt["tgt"].sum()) == int((tgt != -1).sum())
+
+
 def test_metrics_and_compute_iou_acc_vs_reference(mods, golden):
     g = golden("metrics")
     C = int(g["C"])
@@ -567,7 +589,13 @@ def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
 
 
 @pytest.mark.parametrize("shape", [(2, 5, 8, 8, 32, 32), (1, 3, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32),
-                                   (2, 150, 32, 32, 128, 128), (1, 1, 6, 6, 6, 6), (1, 2, 9, 7, 5, 4)])
+                                   (2, 150, 32, 32, 128, 128), (1, 1, 6, 6, 6, 6), (1, 2, 9, 7, 5, 4),
+                                   # exact x2 / x8 (decode-head pyramid), narrow, odd and multi-warp widths
+                                   (2, 7, 16, 16, 32, 32), (2, 7, 16, 16, 128, 128), (1, 3, 7, 9, 14, 18),
+                                   (1, 3, 5, 61, 10, 122), (1, 2, 33, 32, 66, 64), (1, 2, 3, 70, 24, 560),
+                                   (1, 2, 1, 1, 8, 8), (1, 2, 1, 1, 2, 2), (1, 3, 70, 5, 140, 10), (1, 2, 40, 3, 320, 24),
+                                   # PSP pools of the head: 1, 2, 3, 6 -> 16
+                                   (1, 4, 1, 1, 16, 16), (1, 4, 2, 2, 16, 16), (1, 4, 3, 3, 16, 16), (1, 4, 6, 6, 16, 16)])
 def test_upsample_bilinear_vs_torch(mods, shape):
     """robseg_upsample_bilinear_fwd/_bwd vs F.interpolate(..., 'bilinear', align_corners=False) and
     its autograd backward; the backward is a gather, so repeated runs are bit-identical."""
@@ -592,16 +620,56 @@ def test_upsample_bilinear_vs_torch(mods, shape):
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
 
 
+@pytest.mark.parametrize("ratio", [2, 4, 8, 3])
+def test_upsample_backward_reads_cat_slices_in_place(mods, ratio):
+    """The decode head concatenates its up-sampled maps: the gradient of each is a channel slice of
+    the concatenated gradient.  robseg_upsample_bilinear_bwd_strided reads it without a copy."""
+    g = torch.Generator().manual_seed(ratio)
+    h, w = 6, 10
+    xs = [torch.randn(2, 3, h, w, generator=g).to(dev()).requires_grad_() for _ in range(3)]
+    go = torch.randn(2, 9, ratio * h, ratio * w, generator=g).to(dev())
+    ours = torch.cat([mods.ops.upsample_bilinear(x, (ratio * h, ratio * w)) for x in xs], 1)
+    g_ours = torch.autograd.grad(ours, xs, grad_outputs=go)
+    ref = torch.cat([torch.nn.functional.interpolate(x, size=(ratio * h, ratio * w), mode="bilinear",
+                                                     align_corners=False) for x in xs], 1)
+    g_ref = torch.autograd.grad(ref, xs, grad_outputs=go)
+    for a, b in zip(g_ours, g_ref):
+        assert rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+    sl = go[:, 3:6]
+    assert not sl.is_contiguous()
+    assert torch.equal(mods.ops._upsample_bwd(sl, h, w), mods.ops._upsample_bwd(sl.contiguous(), h, w))
+
+
+def test_interpolate_dispatcher_falls_through(mods):
+    x = torch.randn(1, 2, 4, 4, device=dev())
+    F = torch.nn.functional
+    with mods.ops.patched_interpolate():
+        assert F.interpolate is mods.ops.interpolate
+        a = F.interpolate(x, size=(8, 8), mode="bilinear", align_corners=False)  # robseg kernel
+        b = F.interpolate(x, size=(8, 8), mode="bilinear", align_corners=True)   # stock
+        c = F.interpolate(x, scale_factor=2, mode="nearest")                      # stock
+        d = F.interpolate(x.double(), size=(8, 8), mode="bilinear", align_corners=False)  # stock (fp64)
+    assert F.interpolate is not mods.ops.interpolate
+    assert rel(a.cpu().numpy(), F.interpolate(x, size=(8, 8), mode="bilinear", align_corners=False).cpu().numpy()) <= 2e-6
+    assert torch.equal(b, F.interpolate(x, size=(8, 8), mode="bilinear", align_corners=True))
+    assert torch.equal(c, F.interpolate(x, scale_factor=2, mode="nearest")) and d.dtype == torch.float64
+
+
 def test_fast_upsample_consumer_matches_stock(mods):
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
     m = mods.consumers.upernet_convnext("T", 21).to(dev()).eval()
-    x = torch.rand(1, 3, 64, 64, device=dev())
-    with torch.no_grad():
-        a = m(x)
-        m.fast_upsample = True
-        b = m(x)
-    assert rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+    x = torch.rand(1, 3, 64, 64, device=dev(), requires_grad=True)
+    up = torch.randn(1, 21, 64, 64, device=dev())
+    outs, grads = [], []
+    for mode in (False, True, "all"):
+        m.fast_upsample = mode
+        o = m(x)
+        outs.append(o.detach())
+        grads.append(torch.autograd.grad(o, [x], grad_outputs=up)[0])
+    for o, gr in zip(outs[1:], grads[1:]):
+        assert rel(o.cpu().numpy(), outs[0].cpu().numpy()) <= 1e-5
+        assert rel(gr.cpu().numpy(), grads[0].cpu().numpy()) <= 1e-4
 
 
 def test_config1_scaled_upernet_gpu_vs_oracle_cpu(mods):
