@@ -404,8 +404,8 @@ def run_micro(args, mods, dev, rank, world):
         low = torch.randn(Bu, C, S // 4, S // 4, device=dev, generator=g)
         gup = torch.randn(Bu, C, S, S, device=dev, generator=g)
         nb = 4 * (low.numel() + gup.numel())
-        time_it("upsample_fwd x4 (ours)", lambda: ops._upsample_fwd(low, S, S), nb)
-        time_it("upsample_bwd x4 (ours)", lambda: ops._upsample_bwd(gup, S // 4, S // 4), nb)
+        time_it("upsample_fwd x4 (ours)", lambda: ops._upsample_fwd(low, S, S), nb, "upsample_fwd")
+        time_it("upsample_bwd x4 (ours)", lambda: ops._upsample_bwd(gup, S // 4, S // 4), nb, "upsample_bwd")
         time_it("upsample_fwd x4 (ATen)", lambda: F.interpolate(low, size=(S, S), mode="bilinear", align_corners=False), nb)
         lr = low.clone().requires_grad_()
         up = F.interpolate(lr, size=(S, S), mode="bilinear", align_corners=False)
