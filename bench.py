@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--n-iter", type=int, default=10)
     ap.add_argument("--eps", type=float, default=8.0)
-    ap.add_argument("--variant", default="T")
+    ap.add_argument("--variant", default=None, help="ConvNeXt T|S (upernet) or ViT S|B|L (segmenter)")
+    ap.add_argument("--model", default="upernet", choices=["upernet", "segmenter"],
+                    help="consumer: configs[1] UperNet-ConvNeXt (default) or configs[2] Segmenter-ViT")
     ap.add_argument("--micro", action="store_true", help="config-5 kernel microbench instead of the SEA step")
     ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
@@ -57,7 +59,10 @@ def parse():
     ap.add_argument("--logit-upsample-only", action="store_true",
                     help="robseg kernels for the final logit up-sampling only, F.interpolate inside the decode head")
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.variant is None:
+        args.variant = "T" if args.model == "upernet" else "S"
+    return args
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -188,8 +193,12 @@ def run_ours(args):
         return run_micro(args, mods, dev, rank, world)
 
     torch.manual_seed(0)
-    model = mods["consumers"].upernet_convnext(args.variant, args.classes,
-                                               fast_upsample=upsample_mode(args)).to(dev).eval()
+    if args.model == "segmenter":
+        model = mods["consumers"].segmenter_vit(args.variant, args.classes, args.size,
+                                                fast_upsample=bool(upsample_mode(args))).to(dev).eval()
+    else:
+        model = mods["consumers"].upernet_convnext(args.variant, args.classes,
+                                                   fast_upsample=upsample_mode(args)).to(dev).eval()
     for p in model.parameters():
         p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
     B, C, S = args.batch, args.classes, args.size
@@ -265,9 +274,12 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"configs[1]: full SEA (mask-ce-bal, mask-ce-avg, js-avg) x apgd_largereps n_iter={args.n_iter} "
-                        f"(3/3/4 @ 2eps/1.5eps/eps), UperNet-ConvNeXt-{args.variant}_CVST random init, "
-                        f"{C} classes, {S}x{S}, batch {B} per GPU, eps {args.eps:g}/255",
+            "workload": ("configs[1]" if args.model == "upernet" else "configs[2]") +
+                        f": full SEA (mask-ce-bal, mask-ce-avg, js-avg) x apgd_largereps n_iter={args.n_iter} "
+                        f"({'/'.join(map(str, stage_iters(args.n_iter)))} @ 2eps/1.5eps/eps), " +
+                        (f"UperNet-ConvNeXt-{args.variant}_CVST" if args.model == "upernet" else
+                         f"Segmenter-ViT-{args.variant}/16 + mask transformer") +
+                        f" random init, {C} classes, {S}x{S}, batch {B} per GPU, eps {args.eps:g}/255",
             "image_iterations_per_step": iters_per_step * world,
             "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + (1 if args.reforward else 0)),
             "model_bwd_per_step": len(LOSSES) * args.n_iter,
@@ -297,7 +309,7 @@ def run_ours(args):
                      "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
                      "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.model == "upernet":
         line["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -321,6 +333,12 @@ def load_traffic(key):
 
 
 # ------------------------------------------------------------------------------ microbench
+def stage_iters(n_iter):
+    """apgd_largereps' three-stage split (semseg/attacker.py:693-694)."""
+    a = int(0.3 * n_iter)
+    return [a, a, n_iter - 2 * a]
+
+
 def upsample_mode(args):
     """consumers.UperNetConvNeXt.fast_upsample value for the command line."""
     return False if args.stock_upsample else (True if args.logit_upsample_only else "all")

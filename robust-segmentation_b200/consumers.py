@@ -9,6 +9,8 @@ stock cuDNN / cuBLAS.
 the logits to the input size), random-initialised -- there is no network for checkpoints.
 Shapes follow the published ConvNeXt / UperNet designs (depths 3-3-9-3 or 3-3-27-3, widths
 96-192-384-768, PSP pool scales 1-2-3-6, 512 decoder channels, 256-channel FCN aux head).
+``segmenter_vit(variant, n_cls)`` is config 3's Segmenter (ViT-S/16: 384 wide, 6 heads, 12 layers;
+mask-transformer decoder with 2 layers; x16 bilinear up-sampling of the class masks).
 """
 import torch
 import torch.nn as nn
@@ -129,6 +131,80 @@ class UperNetConvNeXt(nn.Module):
 
 def upernet_convnext(variant="T", n_cls=150, fast_upsample=False):
     return UperNetConvNeXt(variant, n_cls, fast_upsample)
+
+
+VIT = {"S": (384, 6, 12), "B": (768, 12, 12), "L": (1024, 16, 24)}  # width, heads, layers (patch 16)
+
+
+class TokenBlock(nn.Module):
+    """Pre-norm transformer block (attention through F.scaled_dot_product_attention)."""
+
+    def __init__(self, dim, heads, hidden):
+        super().__init__()
+        self.heads = heads
+        self.norm1, self.norm2 = nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.qkv, self.proj = nn.Linear(dim, 3 * dim), nn.Linear(dim, dim)
+        self.fc1, self.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        B, N, D = x.shape
+        q, k, v = self.qkv(self.norm1(x)).view(B, N, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
+        x = x + self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D))
+        return x + self.fc2(F.gelu(self.fc1(self.norm2(x))))
+
+
+class SegmenterViT(nn.Module):
+    """Segmenter (ViT encoder, patch 16, + 2-layer mask-transformer decoder, bilinear x16 up-sampling
+    of the class masks to the input size): the architecture BASELINE.json's config 3 names, random
+    init.  ``fast_upsample`` routes the up-sampling through robseg's kernels."""
+
+    def __init__(self, variant="S", n_cls=150, image_size=512, dec_layers=2, fast_upsample=False):
+        super().__init__()
+        dim, heads, layers = VIT[variant]
+        self.patch, self.n_cls, self.fast_upsample = 16, n_cls, fast_upsample
+        self.embed = nn.Conv2d(3, dim, 16, 16)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos = nn.Parameter(torch.zeros(1, 1 + (image_size // 16) ** 2, dim))
+        self.encoder = nn.Sequential(*[TokenBlock(dim, heads, 4 * dim) for _ in range(layers)])
+        self.enc_norm = nn.LayerNorm(dim)
+        self.proj_dec = nn.Linear(dim, dim)
+        self.cls_emb = nn.Parameter(torch.zeros(1, n_cls, dim))
+        self.decoder = nn.Sequential(*[TokenBlock(dim, heads, 4 * dim) for _ in range(dec_layers)])
+        self.dec_norm = nn.LayerNorm(dim)
+        self.proj_patch = nn.Parameter(dim ** -0.5 * torch.randn(dim, dim))
+        self.proj_classes = nn.Parameter(dim ** -0.5 * torch.randn(dim, dim))
+        self.mask_norm = nn.LayerNorm(n_cls)
+        for t in (self.cls_token, self.pos, self.cls_emb):
+            nn.init.trunc_normal_(t, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        B, _, H, W = x.shape
+        gh, gw = H // self.patch, W // self.patch
+        if (gh * gw + 1) != self.pos.shape[1] or H % self.patch or W % self.patch:
+            raise ValueError("SegmenterViT was built for a different image size")
+        t = self.embed(x).flatten(2).transpose(1, 2)
+        t = torch.cat([self.cls_token.expand(B, -1, -1), t], 1) + self.pos
+        t = self.enc_norm(self.encoder(t))[:, 1:]
+        t = torch.cat([self.proj_dec(t), self.cls_emb.expand(B, -1, -1)], 1)
+        t = self.dec_norm(self.decoder(t))
+        patches, classes = t[:, :-self.n_cls] @ self.proj_patch, t[:, -self.n_cls:] @ self.proj_classes
+        patches = patches / patches.norm(dim=-1, keepdim=True)
+        classes = classes / classes.norm(dim=-1, keepdim=True)
+        masks = self.mask_norm(patches @ classes.transpose(1, 2))
+        low = masks.transpose(1, 2).reshape(B, self.n_cls, gh, gw)
+        if self.fast_upsample and low.is_cuda and low.dtype == torch.float32:
+            from . import ops
+
+            return ops.upsample_bilinear(low, (H, W))
+        return F.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)
+
+
+def segmenter_vit(variant="S", n_cls=150, image_size=512, fast_upsample=False):
+    return SegmenterViT(variant, n_cls, image_size, fast_upsample=fast_upsample)
 
 
 class TinySegNet(nn.Module):

@@ -1,5 +1,5 @@
 """Where the consumer's forward/backward time goes (torch.profiler, grouped by op and input shape).
-  python scripts/consumer_profile.py [batch] [classes] [all|logits|stock]"""
+  python scripts/consumer_profile.py [batch] [classes] [all|logits|stock] [upernet|segmenter]"""
 import importlib
 import sys
 
@@ -13,7 +13,10 @@ C = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 mode = {"all": "all", "logits": True, "stock": False}[sys.argv[3] if len(sys.argv) > 3 else "logits"]
-model = consumers.upernet_convnext("T", C, fast_upsample=mode).to(dev).eval()
+if len(sys.argv) > 4 and sys.argv[4] == "segmenter":
+    model = consumers.segmenter_vit("S", C, 512, fast_upsample=bool(mode)).to(dev).eval()
+else:
+    model = consumers.upernet_convnext("T", C, fast_upsample=mode).to(dev).eval()
 x = torch.rand(B, 3, 512, 512, device=dev, requires_grad=True)
 up = torch.randn(B, C, 512, 512, device=dev)
 

@@ -672,6 +672,31 @@ def test_fast_upsample_consumer_matches_stock(mods):
         assert rel(gr.cpu().numpy(), grads[0].cpu().numpy()) <= 1e-4
 
 
+def test_segmenter_consumer_x16_upsample_and_attack(mods):
+    """BASELINE config 3's consumer (Segmenter ViT-S/16 + mask transformer): the x16 up-sampling of
+    its class masks through robseg's kernels equals F.interpolate, forward and gradient; a short
+    SEA attack through the drop-in API lowers the accuracy and stays inside the eps-ball."""
+    torch.manual_seed(0)
+    C, S = 21, 64
+    m = mods.consumers.segmenter_vit("S", C, S).to(dev()).eval()
+    x = torch.rand(2, 3, S, S, device=dev(), requires_grad=True)
+    up = torch.randn(2, C, S, S, device=dev())
+    res = []
+    for fast in (False, True):
+        m.fast_upsample = fast
+        o = m(x)
+        res.append((o.detach(), torch.autograd.grad(o, [x], grad_outputs=up)[0]))
+    assert rel(res[1][0].cpu().numpy(), res[0][0].cpu().numpy()) <= 1e-5
+    assert rel(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) <= 1e-4
+    with torch.no_grad():
+        y = m(x).argmax(1)
+    x_adv, lb, acc = mods.attacker.apgd_largereps(m, x.detach(), y, None, norm="Linf", eps=8 / 255, n_iter=10,
+                                                  loss="mask-ce-avg", track_loss="ce-avg", use_rs=True,
+                                                  early_stop=True, num_classes=C)
+    assert float((x_adv - x.detach()).abs().max()) <= 8 / 255 + 1e-6
+    assert float(acc.mean()) < 0.9  # clean accuracy is 1.0 by construction
+
+
 def test_config1_scaled_upernet_gpu_vs_oracle_cpu(mods):
     """BASELINE config 1 scaled down (UperNet-ConvNeXt-T_CVST random init, 21 classes, Mask-CE,
     apgd_largereps n_iter=10 -> 3/3/4, eps 4/255, 2 images) on the GPU through the drop-in API vs the
