@@ -26,9 +26,25 @@ x = torch.rand(3, 3, 17, 19, generator=g).to(dev)
 ops.apgd_step(x, x.clone(), x.clone(), torch.randn_like(x), torch.full((3,), 0.05, device=dev), 0.03, 0.75, torch.empty_like(x))
 ops.project_linf(x + 0.1, x, 0.03); ops.project_linf(None, x, 0.03, noise=torch.rand_like(x))
 d = torch.zeros_like(x); ops.pgd_step(x, d, torch.randn_like(x), 0.01, 0.03, mask_outside=True, x_next=torch.empty_like(x))
-for shp in [(1, 3, 8, 8, 32, 32), (1, 2, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32), (1, 35, 33, 31, 132, 124)]:
+for shp in [(1, 3, 8, 8, 32, 32), (1, 2, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32), (1, 35, 33, 31, 132, 124),
+            (1, 3, 7, 9, 14, 18), (1, 2, 5, 61, 10, 122), (2, 3, 16, 16, 128, 128), (1, 2, 3, 5, 48, 80), (1, 2, 1, 1, 16, 16),
+            (1, 2, 6, 6, 16, 16), (1, 2, 33, 32, 66, 64)]:
     a = torch.randn(*shp[:4], generator=g).to(dev).requires_grad_()
     o = ops.upsample_bilinear(a, shp[4:]); o.sum().backward()
+# gradient read in place from a channel slice of a concatenated gradient (strided planes)
+aa = [torch.randn(2, 3, 6, 10, generator=g).to(dev).requires_grad_() for _ in range(2)]
+torch.cat([ops.upsample_bilinear(t, (12, 20)) for t in aa], 1).square().sum().backward()
+# histogram kernels: blocks crossing image boundaries, odd plane sizes, several folds of the byte counters
+for n, C, H, W in [(5, 150, 37, 41), (3, 21, 128, 130), (2, 513, 16, 16), (1, 150, 600, 512), (1, 700, 8, 8)]:
+    tt = torch.randint(-1, C, (n, H, W), generator=g).to(dev)
+    pp = torch.where(torch.rand(n, H, W, generator=g).to(dev) < 0.5, tt.clamp(min=0), torch.randint(0, C, (n, H, W), generator=g).to(dev))
+    ops.pixel_hist(pp, tt, C)
+    if C <= 226:
+        ops.pixel_hist(pp, tt, C, want_hist=True)
+os.environ["ROBSEG_CNT_PER_SM"] = "1"
+tt = torch.randint(0, 150, (40, 512, 512), generator=g).to(dev)  # > 240 pixels per lane: folds inside the loop
+ops.pixel_hist(tt.flip(0), tt, 150)
+os.environ.pop("ROBSEG_CNT_PER_SM")
 model = cons.TinySegNet(7, seed=1).to(dev).eval()
 xx = torch.rand(2, 3, 16, 16, generator=g).to(dev)
 yy = model(xx).argmax(1)
