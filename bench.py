@@ -58,6 +58,8 @@ def parse():
                     help="keep F.interpolate for every bilinear up-sampling of the consumer (default: robseg kernels)")
     ap.add_argument("--logit-upsample-only", action="store_true",
                     help="robseg kernels for the final logit up-sampling only, F.interpolate inside the decode head")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the consumer's forward / input-gradient backward as CUDA graphs (SURVEY 8f-4)")
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
     args = ap.parse_args()
     if args.variant is None:
@@ -179,7 +181,7 @@ def run_ours(args):
 
     mods = {k: import_module("robseg_b200." + v) for k, v in dict(
         attacker="semseg.attacker", ops="ops", dist="dist", lib="_lib", consumers="consumers",
-        worse="tools.worse_only").items()}
+        worse="tools.worse_only", graphs="graphs").items()}
     mods["lib"].load()  # fails loudly if the CUDA extension is missing
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -202,6 +204,8 @@ def run_ours(args):
     for p in model.parameters():
         p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
     B, C, S = args.batch, args.classes, args.size
+    if args.graph:
+        model = mods["graphs"].GraphedModel(model, torch.rand(B, 3, S, S, device=dev))
     w = (0.5 + torch.rand(C, generator=torch.Generator().manual_seed(1))).to(dev)  # class-balance weights
     x, y = make_batch(B, C, S, 100 + rank, dev)
     hx, hy = make_batch(B, C, S, 100 + rank, pin=True)
@@ -285,7 +289,8 @@ def run_ours(args):
             "model_bwd_per_step": len(LOSSES) * args.n_iter,
             "adversarial_argmax": "re-forward of x_adv (tools/infer.py:82-90)" if args.reforward else
             "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)",
-            "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)",
+            "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)" +
+                        (", forward / input-gradient backward replayed as CUDA graphs" if args.graph else ""),
             "bilinear_upsample": {False: "F.interpolate (stock) everywhere",
                                   True: "robseg_upsample_bilinear_fwd/_bwd for the final logit up-sampling (SURVEY 8f-1)",
                                   "all": "robseg_upsample_bilinear_fwd/_bwd for the final logit up-sampling (SURVEY 8f-1) "

@@ -42,13 +42,14 @@ class _timed:
         self.name, self.nbytes = name, nbytes
 
     def __enter__(self):
-        if _prof is not None:
+        self.on = _prof is not None and not torch.cuda.is_current_stream_capturing()
+        if self.on:
             self.s = torch.cuda.Event(enable_timing=True)
             self.e = torch.cuda.Event(enable_timing=True)
             self.s.record()
 
     def __exit__(self, *a):
-        if _prof is not None:
+        if self.on and _prof is not None:
             self.e.record()
             _prof.append((self.name, self.nbytes, self.s, self.e))
 

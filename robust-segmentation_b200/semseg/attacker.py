@@ -218,20 +218,29 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
 
     keep_pred = verbose or return_pred
 
+    graphed = hasattr(model, "input_grad")  # graphs.GraphedModel: replayed forward / input gradient
+
     def forward_backward(x_in_buf, need_grad, dbuf):
-        x_in = x_in_buf.detach().requires_grad_(need_grad)
-        with torch.set_grad_enabled(need_grad):
-            logits = model(x_in)
+        if graphed:
+            logits = model(x_in_buf)
+        else:
+            x_in = x_in_buf.detach().requires_grad_(need_grad)
+            with torch.set_grad_enabled(need_grad):
+                logits = model(x_in)
         out = ops.loss_fwd_bwd(logits, y, loss, w_dev, want_grad=need_grad, want_pred=keep_pred,
                                dlogits_out=dbuf)
         g = None
         if need_grad:
-            (g,) = torch.autograd.grad(logits, [x_in], grad_outputs=out.dlogits)
+            if graphed:
+                g = model.input_grad(out.dlogits).clone()
+            else:
+                (g,) = torch.autograd.grad(logits, [x_in], grad_outputs=out.dlogits)
         track = _track_values(out, loss, track_loss, logits, y, w_dev)
         return out, g, track, logits
 
     # ---- initial point (attacker.py:342-383) ------------------------------------------------
-    out, grad, track, logits = forward_backward(x_adv, True, None)
+    # (a graphed model hands out its static gradient buffer: the loss kernel writes into it)
+    out, grad, track, logits = forward_backward(x_adv, True, model.gout if graphed else None)
     dbuf = out.dlogits  # reused every iteration: the model backward has consumed it by then
     n_cls = logits.shape[1]
     del logits

@@ -24,7 +24,7 @@ def mods(pkg):
         pytest.skip("no CUDA device")
     names = dict(ops=".ops", lib="._lib", attacker=".semseg.attacker", val=".semseg.val",
                  metrics=".semseg.metrics", losses=".semseg.losses", worse=".tools.worse_only",
-                 infer=".tools.infer", consumers=".consumers")
+                 infer=".tools.infer", consumers=".consumers", graphs=".graphs")
     return type("M", (), {k: import_module("robseg_b200" + v) for k, v in names.items()})
 
 
@@ -670,6 +670,49 @@ def test_fast_upsample_consumer_matches_stock(mods):
     for o, gr in zip(outs[1:], grads[1:]):
         assert rel(o.cpu().numpy(), outs[0].cpu().numpy()) <= 1e-5
         assert rel(gr.cpu().numpy(), grads[0].cpu().numpy()) <= 1e-4
+
+
+def test_graphed_model_attack_equals_eager(mods):
+    """the consumer's forward / input-gradient backward replayed as CUDA graphs gives the
+    attack the same logits and gradients, hence the same adversarial batch."""
+    graphs = mods.graphs
+    torch.backends.cudnn.allow_tf32 = False
+    C, S = 7, 32
+    model = mods.consumers.TinySegNet(C, seed=3).to(dev()).eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(3, 3, S, S, generator=g).to(dev())
+    with torch.no_grad():
+        y = model(x).argmax(1)
+    gm = graphs.GraphedModel(model, x)
+    xr = x.clone().requires_grad_()
+    o = model(xr)
+    up = torch.randn(o.shape, generator=torch.Generator().manual_seed(1)).to(dev())
+    (gref,) = torch.autograd.grad(o, [xr], grad_outputs=up)
+    assert torch.equal(gm(x), o.detach())
+    # cuDNN may pick another data-gradient algorithm while capturing: equal to rounding, not bitwise
+    assert rel(gm.input_grad(up).cpu().numpy(), gref.cpu().numpy()) <= 1e-5
+    assert all(p.requires_grad for p in model.parameters())
+    outs = []
+    for m in (model, gm):
+        torch.manual_seed(5)
+        outs.append(mods.attacker.apgd_largereps(m, x, y, None, norm="Linf", eps=8 / 255, n_iter=10, loss="mask-ce-avg",
+                                                 track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C,
+                                                 return_pred=True))
+    (xa, la, aa, pa), (xb, lb, ab, pb) = outs
+    # sign(grad) can flip where |grad| ~ 0 (north_star: perturbations match except there)
+    assert float(((xa - xb).abs() > 1e-6).float().mean()) <= 0.02
+    assert float((aa - ab).abs().max()) <= 3 / (S * S) + 1e-7
+    np.testing.assert_allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=2e-2)
+    assert float((pa != pb).float().mean()) <= 0.01
+    # replaying is deterministic
+    torch.manual_seed(5)
+    again = mods.attacker.apgd_largereps(gm, x, y, None, norm="Linf", eps=8 / 255, n_iter=10, loss="mask-ce-avg",
+                                         track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C,
+                                         return_pred=True)
+    for a, b in zip(again, outs[1]):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        gm(x[:2])
 
 
 def test_segmenter_consumer_x16_upsample_and_attack(mods):
