@@ -8,6 +8,8 @@ B, C, S, kind, grad = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
 z = 3 * torch.randn(B, C, S, S, device=dev, generator=g)
+if len(sys.argv) > 6 and sys.argv[6] == "bf16":
+    z = z.bfloat16()
 y = torch.randint(0, C, (B, S, S), device=dev, generator=g)
 y = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.5, z.argmax(1), y)
 d = torch.empty_like(z) if grad else None
@@ -20,5 +22,5 @@ for i in range(6):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 ms = sorted(ts)[len(ts) // 2]
-nbytes = (2 if grad else 1) * z.numel() * 4 + 8 * y.numel()
+nbytes = (2 if grad else 1) * z.numel() * z.element_size() + 8 * y.numel()
 print(f"{sys.argv[1:]} {ms:.3f} ms {nbytes / ms / 1e6:.0f} GB/s", flush=True)
