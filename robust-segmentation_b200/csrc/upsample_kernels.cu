@@ -361,6 +361,150 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- any up-sampling ratio >= 1 (e.g. 119 -> 473, the reference's PASCAL-VOC crops) -----------
+// Same walk-down gather as the power-of-two kernel, with the output pixels assigned to cells by
+// their FIRST tap: output X belongs to cell i0(X) (to the virtual cell -1 while the source
+// coordinate is clamped at the left border), so it feeds cell own with weight wc and cell own+1
+// with weight wr.  A lane owns one cell column and the <= RMAX outputs per row that belong to it;
+// cell b needs its own partial sum plus its left neighbour's wr-sum: ONE shuffle, and only a left
+// halo lane (lane 0).  Rows are walked the same way: the y-table holds, per output row, its cell
+// row and the two weights; a cell row is emitted when the walk leaves it.
+__device__ __forceinline__ int owner_of(int dst, float scale, int in_size) {
+  const float src = scale * ((float)dst + 0.5f) - 0.5f;
+  return src < 0.f ? -1 : min((int)src, in_size - 1);
+}
+// first output index whose owner is >= cell (monotone in dst), exact against owner_of
+__device__ __forceinline__ int first_owned(int cell, float scale, float inv_scale, int in_size,
+                                           int out_size) {
+  int x = (int)ceilf(((float)cell + 0.5f) * inv_scale - 0.5f);
+  x = max(0, min(x, out_size));
+  while (x > 0 && owner_of(x - 1, scale, in_size) >= cell) --x;
+  while (x < out_size && owner_of(x, scale, in_size) < cell) ++x;
+  return x;
+}
+
+struct RowTap {
+  int cell;      // owner cell row (-1: clamped rows, they only feed cell 0)
+  float wc, wn;  // weights for cell `cell` and cell `cell + 1`
+};
+
+template <int RMAX>
+__global__ void __launch_bounds__(256)
+    upsample_bwd_walk_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes,
+                             int C, int64_t bs, int64_t cs, int h, int w, int H, int W, float sy,
+                             float sx, int strip) {
+  constexpr int G = RMAX <= 3 ? 4 : 2;  // output rows in flight
+  extern __shared__ __align__(16) unsigned char walk_smem[];
+  RowTap* ytab = reinterpret_cast<RowTap*>(walk_smem);
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = gw * 31 + lane - 1;  // lane 0: left halo (cell -1 = the clamped outputs for gw == 0)
+  const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
+  // output rows that touch cell rows [a0, a1): owners a0-1 .. a1-1
+  const float inv_sy = 1.f / sy, inv_sx = 1.f / sx;
+  const int Y0 = first_owned(a0 - 1, sy, inv_sy, h, H), Y1 = first_owned(a1, sy, inv_sy, h, H);
+  for (int i = threadIdx.x; i < Y1 - Y0; i += blockDim.x) {
+    const int Y = Y0 + i;
+    const Tap t = make_tap(Y, sy, h);
+    RowTap r;
+    r.cell = owner_of(Y, sy, h);
+    if (r.cell < 0) {
+      r.wc = 0.f, r.wn = t.w0 + (t.i1 == 0 ? t.w1 : 0.f);  // clamped: everything goes to cell 0
+    } else {
+      r.wc = t.w0 + (t.i1 == t.i0 ? t.w1 : 0.f);
+      r.wn = t.i1 == t.i0 ? 0.f : t.w1;
+    }
+    ytab[i] = r;
+  }
+  __syncthreads();
+  if (gw * 31 >= w) return;  // whole warp past the image
+  // my outputs per row: [x0, x0 + n), n <= RMAX (guaranteed by the host's choice of RMAX)
+  const bool cell_ok = b >= -1 && b < w;
+  const int x0 = cell_ok ? first_owned(b, sx, inv_sx, w, W) : 0;
+  const int n = cell_ok ? first_owned(b + 1, sx, inv_sx, w, W) - x0 : 0;
+  float wc[RMAX], wr[RMAX];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) {
+    wc[j] = wr[j] = 0.f;
+    if (j < n) {
+      const Tap t = make_tap(x0 + j, sx, w);
+      if (b < 0) {
+        wr[j] = t.w0 + (t.i1 == 0 ? t.w1 : 0.f);
+      } else {
+        wc[j] = t.w0 + (t.i1 == t.i0 ? t.w1 : 0.f);
+        wr[j] = t.i1 == t.i0 ? 0.f : t.w1;
+      }
+    }
+  }
+  const bool owns = b >= 0 && b < w && lane >= 1;
+  const int rows = Y1 - Y0;
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* rowp = gout + (p / C) * bs + (p % C) * cs + (int64_t)Y0 * W + x0;
+    float* outp = gin + p * (int64_t)h * w + b;
+    float acc_cur = 0.f, acc_next = 0.f;
+    int cur = rows > 0 ? ytab[0].cell : 0;
+    float v[G][RMAX];
+    auto load_rows = [&](int r0) {
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j)
+          v[i][j] = (j < n && r0 + i < rows) ? __ldcs(rowp + (int64_t)(r0 + i) * W + j) : 0.f;
+    };
+    load_rows(0);
+    for (int r0 = 0; r0 < rows; r0 += G) {
+      float xr[G];
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        float pc = 0.f, pr = 0.f;
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) pc = fmaf(wc[j], v[i][j], pc), pr = fmaf(wr[j], v[i][j], pr);
+        xr[i] = pc + __shfl_up_sync(0xffffffffu, pr, 1);  // + lane-1's share for my cell
+      }
+      if (r0 + G < rows) load_rows(r0 + G);  // in flight while these rows are folded in
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        if (r0 + i < rows) {
+          const RowTap t = ytab[r0 + i];
+          if (t.cell != cur) {  // the walk leaves cell row `cur`: it has received everything
+            if (owns && cur >= a0 && cur < a1) outp[(int64_t)cur * w] = acc_cur;
+            acc_cur = acc_next, acc_next = 0.f, cur = t.cell;
+          }
+          acc_cur = fmaf(t.wc, xr[i], acc_cur);
+          acc_next = fmaf(t.wn, xr[i], acc_next);
+        }
+      }
+    }
+    if (owns && cur >= a0 && cur < a1) outp[(int64_t)cur * w] = acc_cur;
+    // (acc_next belongs to cell row a1: the next strip's, or none at the bottom border)
+  }
+}
+
+template <int RMAX>
+static int launch_bwd_walk(const float* gout, float* gin, int64_t planes, int C, int64_t bs, int64_t cs,
+                           int h, int w, int H, int W, float sy, float sx, cudaStream_t stream) {
+  const int warps_x = (w + 30) / 31;
+  const int wpb = warps_x < 8 ? warps_x : 8;
+  const int gx = (warps_x + wpb - 1) / wpb;
+  int strip = h >= 128 ? 64 : 32;
+  if (strip > h) strip = h;
+  const int gy = (h + strip - 1) / strip;
+  int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  // rows per strip: (strip + 1) owners, each with <= ceil(1/sy) + 1 rows, plus the clamped rows
+  const size_t rows_max = (size_t)((strip + 2) * (1.0 / sy + 1.0) + 8);
+  const size_t smem = rows_max * sizeof(RowTap);
+  if (smem > 160 * 1024) return -1;  // caller falls back
+  auto kern = upsample_bwd_walk_kernel<RMAX>;
+  if (smem > 48 * 1024)
+    ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(gx, gy, (unsigned)gz), 32 * wpb, smem, stream>>>(gout, gin, planes, C, bs, cs, h, w, H, W,
+                                                              sy, sx, strip);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace robseg
 
 using namespace robseg;
@@ -447,7 +591,16 @@ extern "C" int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N
       default: break;
     }
   }
-  // tile of input cells per CTA: shrink until the staged output region fits ~48 KB
+  if (H >= h && W >= w) {
+    // walk-down gather for any up-sampling ratio whose per-cell output count fits the registers
+    const int per_cell = (int)ceilf((float)W / (float)w) + 1;
+    int rc = -1;
+    if (per_cell <= 3) rc = launch_bwd_walk<3>(gout, gin, planes, C, bs, cs, h, w, H, W, sy, sx, stream);
+    else if (per_cell <= 6) rc = launch_bwd_walk<6>(gout, gin, planes, C, bs, cs, h, w, H, W, sy, sx, stream);
+    else if (per_cell <= 10) rc = launch_bwd_walk<10>(gout, gin, planes, C, bs, cs, h, w, H, W, sy, sx, stream);
+    if (rc >= 0) return rc;
+  }
+  // anything else: tile of input cells per CTA, shrunk until the staged output region fits ~48 KB
   int TY = 8, TX = 32;
   if (TX > w) TX = w;
   if (TY > h) TY = h;

@@ -28,7 +28,8 @@ ops.project_linf(x + 0.1, x, 0.03); ops.project_linf(None, x, 0.03, noise=torch.
 d = torch.zeros_like(x); ops.pgd_step(x, d, torch.randn_like(x), 0.01, 0.03, mask_outside=True, x_next=torch.empty_like(x))
 for shp in [(1, 3, 8, 8, 32, 32), (1, 2, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32), (1, 35, 33, 31, 132, 124),
             (1, 3, 7, 9, 14, 18), (1, 2, 5, 61, 10, 122), (2, 3, 16, 16, 128, 128), (1, 2, 3, 5, 48, 80), (1, 2, 1, 1, 16, 16),
-            (1, 2, 6, 6, 16, 16), (1, 2, 33, 32, 66, 64)]:
+            (1, 2, 6, 6, 16, 16), (1, 2, 33, 32, 66, 64), (1, 2, 30, 30, 119, 119), (1, 2, 14, 14, 119, 119),
+            (1, 2, 59, 60, 119, 121), (1, 1, 70, 5, 100, 9)]:
     a = torch.randn(*shp[:4], generator=g).to(dev).requires_grad_()
     o = ops.upsample_bilinear(a, shp[4:]); o.sum().backward()
 # gradient read in place from a channel slice of a concatenated gradient (strided planes)

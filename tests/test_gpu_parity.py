@@ -594,6 +594,10 @@ def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
                                    (2, 7, 16, 16, 32, 32), (2, 7, 16, 16, 128, 128), (1, 3, 7, 9, 14, 18),
                                    (1, 3, 5, 61, 10, 122), (1, 2, 33, 32, 66, 64), (1, 2, 3, 70, 24, 560),
                                    (1, 2, 1, 1, 8, 8), (1, 2, 1, 1, 2, 2), (1, 3, 70, 5, 140, 10), (1, 2, 40, 3, 320, 24),
+                                   # non-integer ratios of the reference's 473x473 PASCAL-VOC crops (119 -> 473 logits,
+                                   # 14 / 29 / 59 -> 119 pyramid) and other walk-down gather cases
+                                   (2, 5, 119, 119, 473, 473), (1, 3, 14, 14, 119, 119), (1, 3, 29, 29, 59, 59),
+                                   (1, 2, 59, 60, 119, 121), (1, 2, 40, 70, 41, 71), (1, 2, 3, 100, 7, 333), (1, 1, 130, 5, 200, 9),
                                    # PSP pools of the head: 1, 2, 3, 6 -> 16
                                    (1, 4, 1, 1, 16, 16), (1, 4, 2, 2, 16, 16), (1, 4, 3, 3, 16, 16), (1, 4, 6, 6, 16, 16)])
 def test_upsample_bilinear_vs_torch(mods, shape):
