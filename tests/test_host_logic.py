@@ -69,6 +69,49 @@ def test_no_cpu_fallback(mods):
                 assert "robseg_oracle" not in src and "oracle" not in src.replace("oracle/", ""), f
 
 
+def test_interpolate_dispatcher_on_cpu_is_the_stock_function(mods):
+    """ops.interpolate only takes CUDA fp32 bilinear/align_corners=False calls; on the CPU (and for
+    every other mode) it must be exactly torch's function, and the scoped rebinding must undo itself."""
+    F = torch.nn.functional
+    stock = F.interpolate
+    x = torch.randn(1, 2, 4, 5)
+    with mods.ops.patched_interpolate():
+        assert F.interpolate is mods.ops.interpolate
+        a = F.interpolate(x, size=(8, 10), mode="bilinear", align_corners=False)
+        b = F.interpolate(x, scale_factor=2, mode="nearest")
+    assert F.interpolate is stock
+    assert torch.equal(a, stock(x, size=(8, 10), mode="bilinear", align_corners=False))
+    assert torch.equal(b, stock(x, scale_factor=2, mode="nearest"))
+    with pytest.raises(RuntimeError):  # the kernel wrapper itself refuses CPU tensors
+        mods.ops.upsample_bilinear(x, (8, 10))
+
+
+def test_consumers_cpu_shapes_and_fast_flag_is_inert_on_cpu(mods):
+    torch.manual_seed(0)
+    m = mods.consumers.upernet_convnext("T", 7).eval()
+    x = torch.rand(1, 3, 64, 64)
+    with torch.no_grad():
+        a = m(x)
+        m.fast_upsample = "all"  # CPU input: every up-sampling stays F.interpolate
+        b = m(x)
+    assert a.shape == (1, 7, 64, 64) and torch.equal(a, b)
+    s = mods.consumers.segmenter_vit("S", 7, 32, fast_upsample=True).eval()
+    with torch.no_grad():
+        assert s(torch.rand(2, 3, 32, 32)).shape == (2, 7, 32, 32)
+    with pytest.raises(ValueError):
+        s(torch.rand(1, 3, 48, 48))
+
+
+def test_bench_helpers():
+    import bench
+
+    assert bench.stage_iters(10) == [3, 3, 4] and bench.stage_iters(300) == [90, 90, 120]
+    ns = lambda **k: type("A", (), {**dict(stock_upsample=False, logit_upsample_only=False), **k})()
+    assert bench.upsample_mode(ns()) == "all"
+    assert bench.upsample_mode(ns(logit_upsample_only=True)) is True
+    assert bench.upsample_mode(ns(stock_upsample=True)) is False
+
+
 def test_exact_mean_matches_statistics_mean(mods):
     rng = np.random.default_rng(0)
     for _ in range(300):
