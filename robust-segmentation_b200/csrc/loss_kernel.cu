@@ -145,28 +145,62 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
-template <typename T, int VEC, int G, bool PARTIAL>
+// STR (generic path, unaligned rows): the lane's VEC pixels are 32 apart (lane, lane+32, ...)
+// instead of adjacent, so every global access is a coalesced scalar one with no alignment
+// requirement and a lane may be only partly inside the image; shared memory is then read with
+// VEC scalar loads per row instead of one vector load.
+template <typename T, int VEC, int G, bool PARTIAL, bool STR = false>
 __device__ __forceinline__ void process_tile(const LossParams& p, const T* __restrict__ tile,
                                              int tile_idx, int lane, int half,
                                              const PairXch& xch) {
+  static_assert(!STR || G == 1, "strided pixels: one warp per stage");
   constexpr int ROW = 32 * VEC;
+  constexpr int PS = STR ? 32 : 1;  // distance between the lane's pixels
   constexpr int NACC = (VEC >= 4) ? 1 : 4 / VEC;  // independent accumulator sets per pixel
   constexpr int UNR = 8;
   constexpr int kNone = 0x7fffffff;
-  using V = Vec<T, VEC>;
   const int C = p.C;
   const int c_lo = (G == 1) ? 0 : half * ((C + 1) >> 1);
   const int c_hi = (G == 1) ? C : (half == 0 ? ((C + 1) >> 1) : C);
   const int b = tile_idx / p.tiles_per_img;
-  const int64_t px = (int64_t)(tile_idx - b * p.tiles_per_img) * ROW + lane * VEC;
-  const bool inb = PARTIAL ? (px < p.HW) : true;  // HW % VEC == 0: a lane is all in or all out
+  const int lane_px = STR ? lane : lane * VEC;
+  const int64_t px = (int64_t)(tile_idx - b * p.tiles_per_img) * ROW + lane_px;
+  // adjacent pixels: HW % VEC == 0, a lane is all in or all out; strided: per pixel
+  const bool inb = PARTIAL ? (px < p.HW) : true;
+  bool inj[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) inj[j] = (STR && PARTIAL) ? (px + j * PS < p.HW) : inb;
   const int64_t pix = (int64_t)b * p.HW + px;
-  const T* col = tile + lane * VEC;
+  const T* col = tile + lane_px;
   const bool argmax_only = p.kind == ROBSEG_LOSS_ARGMAX;
+  using V = Vec<T, VEC>;
+  auto ldsv = [&](const T* q, float (&v)[VEC]) {
+    if constexpr (STR) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = V::ld1(q + j * PS);
+    } else {
+      V::lds(q, v);
+    }
+  };
+  auto stgv = [&](T* q, const float (&v)[VEC]) {
+    if constexpr (STR) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (inj[j]) {
+          if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float*>(q) + j * PS, v[j]);
+          else V::st1(q + j * PS, v[j]);
+        }
+    } else {
+      if (inb) V::stg(q, v);
+    }
+  };
 
   // labels: issued now, consumed after pass 1
   int y[VEC];
-  if (inb) {
+  if constexpr (STR) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) y[j] = inj[j] ? (int)__ldg(p.labels + pix + j * PS) : p.ignore_index;
+  } else if (inb) {
     if constexpr (VEC == 1) {
       y[0] = (int)__ldg(p.labels + pix);
     } else {
@@ -199,7 +233,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VEC];
-        V::lds(col + (c + u) * ROW, v);
+        ldsv(col + (c + u) * ROW, v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           const bool g = v[j] > m[u % NACC][j];
@@ -211,7 +245,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll 1
     for (; c < c_hi; ++c) {
       float v[VEC];
-      V::lds(col + c * ROW, v);
+      ldsv(col + c * ROW, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const bool g = v[j] > m[0][j] || (v[j] == m[0][j] && c < am[0][j]);
@@ -241,8 +275,8 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
       for (int u = 0; u < UNR; u += 2) {
         float v0[VEC], v1[VEC];
-        V::lds(col + (c + u) * ROW, v0);
-        V::lds(col + (c + u + 1) * ROW, v1);
+        ldsv(col + (c + u) * ROW, v0);
+        ldsv(col + (c + u + 1) * ROW, v1);
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
           m[(u / 2) % NACC][j] = fmax3(m[(u / 2) % NACC][j], v0[j], v1[j]);
@@ -251,7 +285,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll 1
     for (; c < c_hi; ++c) {
       float v[VEC];
-      V::lds(col + c * ROW, v);
+      ldsv(col + c * ROW, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) m[0][j] = fmaxf(m[0][j], v[j]);
     }
@@ -288,7 +322,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
   if (argmax_only) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+      valid[j] = inj[j] && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
       hit[j] = valid[j] && (amx[j] == y[j]);
       n_correct += hit[j], n_valid += valid[j];
     }
@@ -315,7 +349,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VEC];
-        V::lds(col + (c - 1 - u) * ROW, v);
+        ldsv(col + (c - 1 - u) * ROW, v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           s[u % NACC][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
@@ -326,7 +360,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll 1
     for (; c > c_lo; --c) {
       float v[VEC];
-      V::lds(col + (c - 1) * ROW, v);
+      ldsv(col + (c - 1) * ROW, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
@@ -362,11 +396,11 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
     bool any_grad = false;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      valid[j] = inb && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+      valid[j] = inj[j] && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
       hit[j] = valid[j] && (amx[j] == y[j]);
       ys[j] = valid[j] ? y[j] : 0;
       n_correct += hit[j], n_valid += valid[j];
-      const float zy = V::ld1(col + ys[j] * ROW + j);
+      const float zy = V::ld1(col + ys[j] * ROW + j * PS);
       const float ln_s = logf(st[j]) - resid[j] * kLn2;  // lse - m
       const float logp = (zy - mx[j]) - ln_s;            // log softmax_y  (<= 0)
       const float ce = valid[j] ? -logp : 0.f;
@@ -388,7 +422,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       loss_sum += l;
       ce_sum += ce;
       float gs = g_img;
-      if (p.upstream != nullptr && inb) gs *= __ldg(p.upstream + pix + j);
+      if (p.upstream != nullptr && inj[j]) gs *= __ldg(p.upstream + pix + j * PS);
       const float cg = coef * gs;
       kfac[j] = cg / st[j];
       sub[j] = cg;
@@ -396,7 +430,11 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       any_grad |= (cg != 0.f);
     }
     if (p.loss_pix != nullptr && inb && half == 0) {
-      if constexpr (VEC == 1) {
+      if constexpr (STR) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (inj[j]) p.loss_pix[pix + j * PS] = loss[j];
+      } else if constexpr (VEC == 1) {
         p.loss_pix[pix] = loss[0];
       } else if constexpr (VEC == 2) {
         *reinterpret_cast<float2*>(p.loss_pix + pix) = make_float2(loss[0], loss[1]);
@@ -420,7 +458,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
         for (int j = 0; j < VEC; ++j) zero[j] = 0.f;
         if (inb) {
 #pragma unroll 4
-          for (c = c_lo; c < c_hi; ++c, gp += hw) V::stg(gp, zero);
+          for (c = c_lo; c < c_hi; ++c, gp += hw) stgv(gp, zero);
         }
       } else {
         c = c_lo;
@@ -428,38 +466,42 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
         for (; c + UNR <= c_hi; c += UNR) {
           float v[UNR][VEC];
 #pragma unroll
-          for (int u = 0; u < UNR; ++u) V::lds(col + (c + u) * ROW, v[u]);
+          for (int u = 0; u < UNR; ++u) ldsv(col + (c + u) * ROW, v[u]);
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
             float g[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
               g[j] = ex2_approx(fmaf(v[u][j], kLog2e, -mL[j])) * kfac[j];
-            if (inb) V::stg(gp, g);
+            stgv(gp, g);
             gp += hw;
           }
         }
 #pragma unroll 1
         for (; c < c_hi; ++c, gp += hw) {
           float v[VEC], g[VEC];
-          V::lds(col + c * ROW, v);
+          ldsv(col + c * ROW, v);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
-          if (inb) V::stg(gp, g);
+          stgv(gp, g);
         }
         // the label channel: coef*(p_y - 1).  Same thread, same address, program order.
         T* gy = reinterpret_cast<T*>(p.dlogits) + (int64_t)b * C * p.HW + px;
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
           if (sub[j] != 0.f && ys[j] >= c_lo && ys[j] < c_hi)
-            V::st1(gy + (int64_t)ys[j] * p.HW + j, fmaf(ey[j], kfac[j], -sub[j]));
+            V::st1(gy + (int64_t)ys[j] * p.HW + j * PS, fmaf(ey[j], kfac[j], -sub[j]));
       }
     }
   }
 
   if (half == 0) {
     if (p.pred != nullptr && inb) {
-      if constexpr (VEC == 1) {
+      if constexpr (STR) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (inj[j]) p.pred[pix + j * PS] = amx[j];
+      } else if constexpr (VEC == 1) {
         p.pred[pix] = amx[0];
       } else {
         longlong2* pp = reinterpret_cast<longlong2*>(p.pred + pix);
@@ -610,6 +652,69 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
       process_tile<float, 1, 1, false>(p, cur, tile, lane, 0, PairXch{});
     else
       process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{});
+    __syncwarp();
+  }
+}
+
+// Wider tiles for the same case: [C][32*VEC] stages filled with 4-byte copies (lane L copies
+// elements L, L+32, ... of every row, whatever the row alignment) and consumed with the lane's
+// VEC pixels 32 apart, so labels, argmax map and gradient are coalesced scalar accesses.  The
+// per-pixel work (label, log, loss terms) and the per-tile reductions are amortised over VEC
+// times more pixels per lane than in the one-pixel kernel above (23 -> ~15 instructions per logit
+// at C = 21).
+template <int VEC>
+__global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossParams p, const int K) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int ROW = 32 * VEC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int stage_elems = p.C * ROW;
+  float* bufs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * K * stage_elems;
+  const float* logits = reinterpret_cast<const float*>(p.logits);
+  auto issue = [&](int tile, float* dst) {
+    const int b = tile / p.tiles_per_img;
+    const int64_t px = (int64_t)(tile - b * p.tiles_per_img) * ROW + lane;
+    const float* src = logits + (int64_t)b * p.C * p.HW + px;
+    int n[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) n[k] = px + 32 * k < p.HW ? 4 : 0;  // src-size 0: zero-fill
+    if (n[0] == 0) src = logits;  // keep the (unused) address valid
+    uint32_t d = smem_u32(dst + lane);
+    const int64_t hw = p.HW;
+#pragma unroll 2
+    for (int c = 0; c < p.C; ++c, src += hw, d += 4 * ROW) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 128 * k),
+                     "l"(n[k] ? src + 32 * k : src), "r"(n[k])
+                     : "memory");
+    }
+    cp_async_commit();
+  };
+  const int stride = gridDim.x * W;
+  int tile = blockIdx.x * W + warp;
+  int k = 0;
+  if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
+  for (; tile < p.num_tiles; tile += stride) {
+    float* cur = bufs + (size_t)k * stage_elems;
+    if (K == 2) {
+      const int next = tile + stride;
+      if (next < p.num_tiles) {
+        issue(next, bufs + (size_t)(k ^ 1) * stage_elems);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      k ^= 1;
+    } else {
+      issue(tile, cur);
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const int tin = tile % p.tiles_per_img;
+    if ((int64_t)(tin + 1) * ROW <= p.HW)
+      process_tile<float, VEC, 1, false, true>(p, cur, tile, lane, 0, PairXch{});
+    else
+      process_tile<float, VEC, 1, true, true>(p, cur, tile, lane, 0, PairXch{});
     __syncwarp();
   }
 }
@@ -765,13 +870,39 @@ static int launch_tma_pick(const LossParams& p, cudaStream_t stream) {
 }
 
 template <typename T>
-static int launch_generic(const LossParams& p0, cudaStream_t stream) {
+static int launch_generic(const LossParams& p0, cudaStream_t stream, int* tiles_per_img) {
   LossParams p = p0;
-  p.tiles_per_img = (int)((p.HW + 31) / 32);
+  p.tiles_per_img = *tiles_per_img = (int)((p.HW + 31) / 32);
   p.num_tiles = p.B * p.tiles_per_img;
   const size_t stage = (size_t)p.C * 32 * sizeof(T);
   ROBSEG_REQUIRE(stage <= kSmemBudget, "C=%d too large for one shared-memory stage", p.C);
   if constexpr (sizeof(T) == 4) {
+    // wide strided tiles while >= 16 warps per SM keep two stages each (C <= 13 at 4 pixels per
+    // lane, <= 27 at 2; measured at 24x21x473x473: 0.27 ms at 2, 0.29-0.35 ms at 4 with 10 warps,
+    // 0.33 ms at 1); otherwise one pixel per lane.  ROBSEG_LOSS_GENERIC_VEC forces a width that
+    // fits 8 warps (tests, experiments).
+    int vec = 4, min_warps = 16;
+    if (const char* e = getenv("ROBSEG_LOSS_GENERIC_VEC")) vec = atoi(e), min_warps = 8;
+    if (vec != 1 && vec != 2 && vec != 4) vec = 4;
+    while (vec > 1 && (size_t)min_warps * 2 * stage * vec > kSmemBudget) vec >>= 1;
+    if (vec > 1) {
+      const size_t st = stage * vec;
+      int warps_sm = (int)(kSmemBudget / (2 * st));
+      if (warps_sm > 32) warps_sm = 32;
+      const int W = 8, ctas_sm = warps_sm / W;
+      const size_t smem = (size_t)W * 2 * st;
+      auto kern = vec == 4 ? loss_generic_strided_kernel<4> : loss_generic_strided_kernel<2>;
+      ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      p.tiles_per_img = *tiles_per_img = (int)((p.HW + 32 * vec - 1) / (32 * vec));
+      p.num_tiles = p.B * p.tiles_per_img;
+      int grid = sm_count() * ctas_sm;
+      const int max_useful = (p.num_tiles + W - 1) / W;
+      if (grid > max_useful) grid = max_useful;
+      if (grid < 1) grid = 1;
+      kern<<<grid, 32 * W, smem, stream>>>(p, 2);
+      ROBSEG_LAUNCH_CHECK();
+      return 0;
+    }
     // as many warps per SM as shared memory allows (<= 64), two stages per warp when they fit
     int warps_sm = (int)(kSmemBudget / stage);
     if (warps_sm > 64) warps_sm = 64;
@@ -864,9 +995,8 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
                                : launch_tma_pick<__nv_bfloat16, 2>(p, stream);
     }
   } else {
-    tiles_per_img = (int)((HW + 31) / 32);
-    rc = dtype == ROBSEG_F32 ? launch_generic<float>(p, stream)
-                             : launch_generic<__nv_bfloat16>(p, stream);
+    rc = dtype == ROBSEG_F32 ? launch_generic<float>(p, stream, &tiles_per_img)
+                             : launch_generic<__nv_bfloat16>(p, stream, &tiles_per_img);
   }
   if (rc != 0) return rc;
   if (loss_img || track_img || correct_img || valid_img) {

@@ -52,7 +52,10 @@ def make_problem(B, C, H, W, seed, sigma=3.0, frac_ignore=0.1, bf16=False):
 # shapes: TMA path VEC=4 (C<=48), VEC=2, VEC=1 (C=150/151), partial last tile, and shapes that
 # force the generic path (HW*4 % 16 != 0)
 SHAPES = [(2, 21, 32, 32), (2, 7, 5, 6), (1, 64, 16, 24), (1, 150, 24, 24), (2, 151, 16, 20),
-          (1, 21, 33, 37), (1, 151, 13, 11), (3, 2, 8, 8), (1, 256, 8, 8), (1, 300, 6, 6)]
+          (1, 21, 33, 37), (1, 151, 13, 11), (3, 2, 8, 8), (1, 256, 8, 8), (1, 300, 6, 6),
+          # odd H*W (rows only 4-byte aligned): the strided generic kernel at 4 / 2 pixels per lane, tiles
+          # crossing the image end, images smaller than one tile
+          (2, 21, 47, 43), (1, 40, 25, 25), (3, 5, 7, 5), (2, 27, 19, 27), (1, 55, 11, 13)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -70,6 +73,38 @@ def test_loss_kernel_vs_oracle_fp32(mods, shape, kind):
     assert rel(out.loss_pix.cpu().numpy().reshape(B, -1), ref["loss_pix"]) <= 1e-5
     np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
     np.testing.assert_allclose(out.track_img.cpu().numpy(), ref["track_img"], rtol=1e-5, atol=1e-8)
+
+
+def test_loss_kernel_voc_shape_generic_paths_agree(mods, monkeypatch):
+    """The reference's PASCAL-VOC shape (473 x 473 crops, 21 classes: odd H*W, no TMA): the strided
+    generic kernels (4 and 2 pixels per lane) and the one-pixel kernel give the same argmax map and
+    counts exactly and the same losses / gradients to rounding; properties at full size."""
+    B, C, S = 6, 21, 473
+    g = torch.Generator(device=dev()).manual_seed(3)
+    z = 3 * torch.randn(B, C, S, S, device=dev(), generator=g)
+    y = torch.randint(-1, C, (B, S, S), device=dev(), generator=g)
+    y = torch.where(torch.rand(B, S, S, device=dev(), generator=g) < 0.5, z.argmax(1), y)
+    w = 0.5 + torch.rand(C, device=dev(), generator=g)
+    for kind in ("mask-ce-bal", "js-avg"):
+        outs = []
+        for vec in ("4", "2", "1"):
+            monkeypatch.setenv("ROBSEG_LOSS_GENERIC_VEC", vec)
+            outs.append(mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_loss_pix=True))
+        monkeypatch.delenv("ROBSEG_LOSS_GENERIC_VEC")
+        ref = outs[2]
+        assert torch.equal(ref.pred, z.argmax(1))
+        for o in outs[:2]:
+            assert torch.equal(o.pred, ref.pred) and torch.equal(o.correct, ref.correct) and torch.equal(o.valid, ref.valid)
+            assert rel(o.dlogits.cpu().numpy(), ref.dlogits.cpu().numpy()) <= 2e-6
+            assert rel(o.loss_pix.cpu().numpy(), ref.loss_pix.cpu().numpy()) <= 2e-6
+            np.testing.assert_allclose(o.loss_img.cpu().numpy(), ref.loss_img.cpu().numpy(), rtol=1e-6)
+            np.testing.assert_allclose(o.track_img.cpu().numpy(), ref.track_img.cpu().numpy(), rtol=1e-6)
+        d = outs[0].dlogits
+        assert float(d.sum(1).abs().max()) <= 1e-6 * float(d.abs().max()) * C  # sum_k dlogits = 0
+        again = mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True)
+        assert torch.equal(again.dlogits, d) and torch.equal(again.loss_img, outs[0].loss_img)  # deterministic
+        lo = mods.ops.loss_fwd_bwd(z, y, kind, w, want_grad=False)
+        assert torch.equal(lo.loss_img, outs[0].loss_img) and torch.equal(lo.correct, outs[0].correct)
 
 
 @pytest.mark.parametrize("tag", ["c7", "c21", "c151"])
