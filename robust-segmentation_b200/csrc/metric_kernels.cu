@@ -373,6 +373,7 @@ extern "C" int robseg_pixel_hist(const int64_t* pred, const int64_t* labels, int
     int64_t pb = (total_px + slots - 1) / slots;
     pb = ((pb + batch_px - 1) / batch_px) * batch_px;
     if (pb < 2 * (int64_t)batch_px) pb = 2 * (int64_t)batch_px;
+    if (pb > ((int64_t)1 << 30)) pb = ((int64_t)1 << 30) / batch_px * batch_px;  // 32-bit offsets inside a piece
     *per_block = pb;
     return (unsigned)((total_px + pb - 1) / pb);
   };
