@@ -145,10 +145,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
-// STR (generic path, unaligned rows): the lane's VEC pixels are 32 apart (lane, lane+32, ...)
-// instead of adjacent, so every global access is a coalesced scalar one with no alignment
-// requirement and a lane may be only partly inside the image; shared memory is then read with
-// VEC scalar loads per row instead of one vector load.
+// STR (generic path, unaligned rows): the lane's VEC pixels are 32 apart in GLOBAL memory (lane,
+// lane+32, ...) instead of adjacent, so every global access is a coalesced scalar one with no
+// alignment requirement and a lane may be only partly inside the image.  The stage is still
+// lane-major (pixel lane+32j at column lane*VEC+j: the 4-byte fill transposes), so shared memory
+// is read with one vector load per row in both modes.
 template <typename T, int VEC, int G, bool PARTIAL, bool STR = false>
 __device__ __forceinline__ void process_tile(const LossParams& p, const T* __restrict__ tile,
                                              int tile_idx, int lane, int half,
@@ -171,17 +172,11 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
   for (int j = 0; j < VEC; ++j) inj[j] = (STR && PARTIAL) ? (px + j * PS < p.HW) : inb;
   const int64_t pix = (int64_t)b * p.HW + px;
-  const T* col = tile + lane_px;
+  // shared memory is lane-major in both modes (the strided fill transposes): one vector load per row
+  const T* col = tile + lane * VEC;
   const bool argmax_only = p.kind == ROBSEG_LOSS_ARGMAX;
   using V = Vec<T, VEC>;
-  auto ldsv = [&](const T* q, float (&v)[VEC]) {
-    if constexpr (STR) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) v[j] = V::ld1(q + j * PS);
-    } else {
-      V::lds(q, v);
-    }
-  };
+  auto ldsv = [&](const T* q, float (&v)[VEC]) { V::lds(q, v); };
   auto stgv = [&](T* q, const float (&v)[VEC]) {
     if constexpr (STR) {
 #pragma unroll
@@ -400,7 +395,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       hit[j] = valid[j] && (amx[j] == y[j]);
       ys[j] = valid[j] ? y[j] : 0;
       n_correct += hit[j], n_valid += valid[j];
-      const float zy = V::ld1(col + ys[j] * ROW + j * PS);
+      const float zy = V::ld1(col + ys[j] * ROW + j);
       const float ln_s = logf(st[j]) - resid[j] * kLn2;  // lse - m
       const float logp = (zy - mx[j]) - ln_s;            // log softmax_y  (<= 0)
       const float ce = valid[j] ? -logp : 0.f;
@@ -657,8 +652,9 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
 }
 
 // Wider tiles for the same case: [C][32*VEC] stages filled with 4-byte copies (lane L copies
-// elements L, L+32, ... of every row, whatever the row alignment) and consumed with the lane's
-// VEC pixels 32 apart, so labels, argmax map and gradient are coalesced scalar accesses.  The
+// elements L, L+32, ... of every row, whatever the row alignment, into ITS columns L*VEC ..) and
+// consumed with the lane's VEC pixels 32 apart, so labels, argmax map and gradient are coalesced
+// scalar accesses while shared memory is read with vector loads.  The
 // per-pixel work (label, log, loss terms) and the per-tile reductions are amortised over VEC
 // times more pixels per lane than in the one-pixel kernel above (23 -> ~15 instructions per logit
 // at C = 21).
@@ -678,13 +674,13 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
 #pragma unroll
     for (int k = 0; k < VEC; ++k) n[k] = px + 32 * k < p.HW ? 4 : 0;  // src-size 0: zero-fill
     if (n[0] == 0) src = logits;  // keep the (unused) address valid
-    uint32_t d = smem_u32(dst + lane);
+    uint32_t d = smem_u32(dst + lane * VEC);  // transposed: pixel lane+32k -> column lane*VEC+k
     const int64_t hw = p.HW;
 #pragma unroll 2
     for (int c = 0; c < p.C; ++c, src += hw, d += 4 * ROW) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 128 * k),
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * k),
                      "l"(n[k] ? src + 32 * k : src), "r"(n[k])
                      : "memory");
     }
