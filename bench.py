@@ -274,7 +274,8 @@ def run_ours(args):
     h2d = B * 3 * S * S * 4 + B * S * S * 8
     d2h = len(LOSSES) * B * 3 * S * S * 4 + B * world * 4
     line = {
-        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if args.model == "upernet" else METRIC.replace("UperNet-ConvNeXt-T", f"Segmenter-ViT-{args.variant}"),
+        "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
