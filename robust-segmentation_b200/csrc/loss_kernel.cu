@@ -258,6 +258,55 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
         amx[j] = g ? am[a][j] : amx[j];
       }
     }
+  } else if constexpr (sizeof(T) == 2 && VEC >= 2) {
+    // bf16: the maximum of packed pairs is exact, so the whole pass runs on the raw words
+    // (HMNMX2.BF16, no unpack): 1 instruction per logit instead of 2
+    constexpr int NW = VEC / 2;
+    __nv_bfloat162 m2[2][NW];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int k = 0; k < NW; ++k) m2[a][k] = ninf;
+    auto ldw = [&](const T* q, __nv_bfloat162 (&wv)[NW]) {
+      if constexpr (NW == 1) {
+        wv[0] = *reinterpret_cast<const __nv_bfloat162*>(q);
+      } else if constexpr (NW == 2) {
+        const uint2 t = *reinterpret_cast<const uint2*>(q);
+        wv[0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        wv[1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+      } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(q);
+        wv[0] = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        wv[1] = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        wv[2] = *reinterpret_cast<const __nv_bfloat162*>(&t.z);
+        wv[3] = *reinterpret_cast<const __nv_bfloat162*>(&t.w);
+      }
+    };
+    int c = c_lo;
+#pragma unroll 1
+    for (; c + UNR <= c_hi; c += UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        __nv_bfloat162 wv[NW];
+        ldw(col + (c + u) * ROW, wv);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) m2[u & 1][k] = __hmax2(m2[u & 1][k], wv[k]);
+      }
+    }
+#pragma unroll 1
+    for (; c < c_hi; ++c) {
+      __nv_bfloat162 wv[NW];
+      ldw(col + c * ROW, wv);
+#pragma unroll
+      for (int k = 0; k < NW; ++k) m2[0][k] = __hmax2(m2[0][k], wv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const __nv_bfloat162 mm = __hmax2(m2[0][k], m2[1][k]);
+      mx[2 * k] = __low2float(mm), mx[2 * k + 1] = __high2float(mm);
+      amx[2 * k] = amx[2 * k + 1] = kNone;
+    }
   } else {
     float m[NACC][VEC];
 #pragma unroll
