@@ -409,6 +409,54 @@ def sea_worst_miou(cons_ints, cons_unions, rng=None, n_rounds=1000):
 # --------------------------------------------------------------------------------------
 # (5) the attack loops, with the model as a black box
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------
+# Bilinear up-sampling of the logits / pyramid maps
+# ------------------------------------------------------------------------------------------
+def _bilinear_taps(out_size, in_size):
+    """Source taps of ``nn.functional.interpolate(..., mode="bilinear", align_corners=False)``
+    as the reference calls it (semseg/models/uperforseg.py:193-198,282-303,416-418;
+    semseg/models/segmenter.py:228).  The arithmetic lives in PyTorch, a dependency of the
+    reference (torch==2.2.0 pinned, requirements.txt:70; 2.11 here, same formula): ATen's
+    ``area_pixel_compute_source_index`` in float32 -- scale = in/out, src = scale*(dst+0.5)-0.5
+    clamped at 0, i0 = floor(src), i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1."""
+    dst = np.arange(out_size, dtype=_f32)
+    scale = _f32(in_size) / _f32(out_size)
+    src = (scale * (dst + _f32(0.5)) - _f32(0.5)).astype(_f32)
+    src = np.maximum(src, _f32(0.0))
+    i0 = np.minimum(src.astype(np.int64), in_size - 1)
+    i1 = i0 + (i0 < in_size - 1)
+    w1 = (src - i0.astype(_f32)).astype(_f32)
+    w0 = (_f32(1.0) - w1).astype(_f32)
+    return i0, i1, w0, w1
+
+
+def upsample_bilinear(x, H, W):
+    """[..., h, w] float32 -> [..., H, W]; float32 products in ATen's order
+    (w0y*(w0x*a + w1x*b) + w1y*(w0x*c + w1x*d))."""
+    x = np.asarray(x, dtype=_f32)
+    y0, y1, wy0, wy1 = _bilinear_taps(H, x.shape[-2])
+    x0, x1, wx0, wx1 = _bilinear_taps(W, x.shape[-1])
+    top = (wx0 * x[..., y0, :][..., :, x0] + wx1 * x[..., y0, :][..., :, x1]).astype(_f32)
+    bot = (wx0 * x[..., y1, :][..., :, x0] + wx1 * x[..., y1, :][..., :, x1]).astype(_f32)
+    return (wy0[:, None] * top + wy1[:, None] * bot).astype(_f32)
+
+
+def upsample_bilinear_bwd(g, h, w):
+    """Adjoint of :func:`upsample_bilinear`: [..., H, W] -> [..., h, w], accumulated in float64
+    (the product's gather and ATen's atomic scatter differ from it only by float32 rounding)."""
+    g = np.asarray(g, dtype=np.float64)
+    H, W = g.shape[-2:]
+    y0, y1, wy0, wy1 = _bilinear_taps(H, h)
+    x0, x1, wx0, wx1 = _bilinear_taps(W, w)
+    My = np.zeros((H, h))
+    np.add.at(My, (np.arange(H), y0), wy0.astype(np.float64))
+    np.add.at(My, (np.arange(H), y1), wy1.astype(np.float64))
+    Mx = np.zeros((W, w))
+    np.add.at(Mx, (np.arange(W), x0), wx0.astype(np.float64))
+    np.add.at(Mx, (np.arange(W), x1), wx1.astype(np.float64))
+    return np.einsum("Yy,...YX,Xx->...yx", My, g, Mx)
+
+
 class TorchModelAdapter:
     """Wraps a torch.nn.Module (CPU, eval) as the black-box consumer the oracle drives:
     ``forward(x) -> logits [B,C,P]`` and ``vjp(dlogits) -> d/dx`` (float32 numpy)."""

@@ -652,6 +652,10 @@ def test_upsample_bilinear_vs_torch(mods, shape):
     (gours,) = torch.autograd.grad(out, [xo], grad_outputs=go)
     assert rel(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 2e-6
     assert rel(gours.cpu().numpy(), gref.cpu().numpy()) <= 1e-5
+    # and against the oracle's restatement of the same interpolation (numpy rounds scale*(dst+0.5)-0.5 in
+    # two steps, the device contracts it into one FMA: the tap weights can differ in the last bit)
+    assert rel(out.detach().cpu().numpy(), O.upsample_bilinear(x.cpu().numpy(), H, W)) <= 1e-5
+    assert rel(gours.cpu().numpy(), O.upsample_bilinear_bwd(go.cpu().numpy(), h, w)) <= 2e-5
     out2 = mods.ops.upsample_bilinear(xo, (H, W))
     (g2,) = torch.autograd.grad(out2, [xo], grad_outputs=go)
     assert torch.equal(g2, gours) and torch.equal(out2, out)

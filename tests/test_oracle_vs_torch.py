@@ -70,3 +70,25 @@ def test_update_kernels_match_torch_fp32_chain():
     zz = x + 0.1 * torch.randn(shape, generator=g)
     ref = (x + (zz - x).clamp(-eps, eps)).clamp(0.0, 1.0)  # semseg/attacker.py:683-690
     assert np.array_equal(O.project_linf(zz.numpy(), x.numpy(), eps), ref.numpy())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 8, 32, 32), (1, 2, 5, 6, 13, 17), (1, 2, 30, 30, 119, 119), (1, 2, 14, 14, 119, 119),
+                                   (1, 1, 6, 6, 6, 6), (1, 2, 1, 1, 16, 16), (1, 2, 9, 7, 5, 4), (1, 2, 32, 32, 512, 512)])
+def test_bilinear_upsampling_restatement_matches_torch(shape):
+    """The oracle's restatement of ATen's bilinear interpolation (align_corners=False), the op the
+    reference's models call for their logits and pyramid maps, against torch itself: forward and
+    the adjoint (autograd) on the CPU."""
+    B, C, h, w, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, C, h, w, generator=g).requires_grad_()
+    go = torch.randn(B, C, H, W, generator=g)
+    ref = torch.nn.functional.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)
+    (gref,) = torch.autograd.grad(ref, [x], go)
+    out = O.upsample_bilinear(x.detach().numpy(), H, W)
+    gin = O.upsample_bilinear_bwd(go.numpy(), h, w)
+    assert np.abs(out - ref.detach().numpy()).max() <= 1e-5 * np.abs(ref.detach().numpy()).max()
+    assert np.abs(gin - gref.numpy()).max() <= 1e-5 * np.abs(gref.numpy()).max()
+    # adjointness of the restatement itself, in float64
+    lhs = float((out.astype(np.float64) * go.numpy()).sum())
+    rhs = float((x.detach().numpy().astype(np.float64) * gin).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
