@@ -10,7 +10,8 @@
  * ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions
- *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - every pointer is a DEVICE pointer unless its name ends in _host (functions named *_host
+ *    take host pointers only and launch nothing);
  *  - the library allocates nothing persistent: the caller owns every buffer and workspace;
  *  - all launches go to the stream passed in (a cudaStream_t cast to void*), no internal
  *    synchronisation;
@@ -214,6 +215,24 @@ int robseg_upsample_bilinear_bwd(const float* gout, int64_t planes, int H, int W
 int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N, int C, int64_t batch_stride,
                                          int64_t chan_stride, int H, int W, float* gin, int h, int w,
                                          robseg_stream_t stream);
+
+/*
+ * HOST functions (every pointer is host memory): the exact arithmetic of the sequential greedy in
+ * evalSEA.worst_case_miou (tools/worse_only.py:267-334) -- SURVEY.md section 8f rank 3.
+ *
+ * robseg_exact_mean_host: statistics.mean(values) -- the correctly rounded mean of the exact sum
+ *   (the reference scores every candidate with it, :69-93).
+ * robseg_sea_greedy_round_host: ONE round of the greedy over the images in order_host[N] (the caller
+ *   shuffles with Python's `random`, as the reference does, :283-285).  cons_ints / cons_unions:
+ *   [A,N,C] float64 exact counts; sel[N] current attack per image; run_int / run_union [C] running
+ *   sums (re-rounded to float32 wherever the reference rebuilds a tensor from its lists,
+ *   :311-316,323-326); *final_miou current value.  All four are updated in place.
+ */
+int robseg_exact_mean_host(const double* values_host, int64_t n, double* mean_host);
+int robseg_sea_greedy_round_host(const double* cons_ints_host, const double* cons_unions_host, int A,
+                                 int N, int C, const int32_t* order_host, int32_t* sel_host,
+                                 double* run_int_host, double* run_union_host,
+                                 double* final_miou_host);
 
 #ifdef __cplusplus
 }

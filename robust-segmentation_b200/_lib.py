@@ -40,6 +40,8 @@ SIGNATURES = {
     "robseg_upsample_bilinear_fwd": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p]),
     "robseg_upsample_bilinear_bwd": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p]),
     "robseg_upsample_bilinear_bwd_strided": (_i, [_p, _i64, _i, _i64, _i64, _i, _i, _p, _i, _i, _p]),
+    "robseg_exact_mean_host": (_i, [_p, _i64, _p]),
+    "robseg_sea_greedy_round_host": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -10,9 +10,10 @@ Worst-case SEA aggregation over the per-attack argmax maps:
   exact sums, min over attacks); only the final means over N images are taken with the
   same ``torch`` CPU ops as the reference so the reported float is bit-identical;
 * the greedy randomised worst-case mIoU (``:267-334``) is inherently sequential and stays on
-  the host.  It replays the reference's arithmetic exactly: float32 running sums, Python
-  double ratios with the ``+1e-8`` in the candidate score, and ``statistics.mean``'s
-  correctly rounded exact mean (computed here with integer arithmetic, ~10x faster).
+  the host, in C++ (``robseg_sea_greedy_round_host``): it replays the reference's arithmetic
+  exactly -- float32 running sums, double ratios with the ``+1e-8`` in the candidate score,
+  and ``statistics.mean``'s correctly rounded exact mean (a fixed-point super-accumulator and
+  one rounding) -- while the shuffles stay with Python's seeded ``random``.
 
 Known deviations: Q5 -- a ragged last batch is indexed correctly
 (the reference's ``i*BS`` offset is wrong there; identical when ``N % bs == 0``); Q8 -- classes
@@ -32,28 +33,24 @@ SEED = 225
 random.seed(SEED)
 np.random.seed(SEED)
 
-_TWO53 = float(2 ** 53)
+def _dptr(a):
+    return a.ctypes.data
 
 
 def exact_mean(values):
-    """Correctly rounded mean of a float64 vector == ``statistics.mean(list)``.
+    """Correctly rounded mean of a float64 vector == ``statistics.mean(list)``
+    (robseg_exact_mean_host: exact fixed-point accumulation, one rounding at the end)."""
+    import ctypes
 
-    Every double is m * 2**e with an integer 53-bit m; the sum is accumulated in Python's
-    arbitrary-precision integers and the final int/int true division is correctly rounded."""
-    values = np.asarray(values, dtype=np.float64)
-    n = values.size
-    if n == 0:
+    from .. import _lib
+
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    if v.size == 0:
         raise ValueError("mean requires at least one data point")
-    mant, exp = np.frexp(values)
-    mi = (mant * _TWO53).astype(np.int64)
-    emin = int(exp.min())
-    total = 0
-    for m, e in zip(mi.tolist(), (exp - emin).tolist()):
-        total += m << e
-    k = emin - 53
-    if k >= 0:
-        return (total << k) / n
-    return total / (n << (-k))
+    out = ctypes.c_double()
+    _lib.check(_lib.load().robseg_exact_mean_host(_dptr(v), v.size, ctypes.addressof(out)),
+               "robseg_exact_mean_host")
+    return out.value
 
 
 def _f32(v):
@@ -67,34 +64,34 @@ def _compute_miou(inters, union):
 
 
 def greedy_worst_miou(cons_ints, cons_unions, n_rounds=1000, rng=random):
-    """tools/worse_only.py:267-334.  cons_*: [A,N,C] exact counts.  Returns (miou, selection)."""
-    ci = np.asarray(cons_ints, dtype=np.float64)
-    cu = np.asarray(cons_unions, dtype=np.float64)
-    A, N, _ = ci.shape
+    """tools/worse_only.py:267-334.  cons_*: [A,N,C] exact counts.  Returns (miou, selection).
+
+    The shuffles come from ``rng`` (Python's ``random``, seeded by the caller as the reference
+    does); each round of the sequential greedy runs in robseg_sea_greedy_round_host with the
+    reference's exact arithmetic."""
+    from .. import _lib
+
+    lib = _lib.load()
+    ci = np.ascontiguousarray(cons_ints, dtype=np.float64)
+    cu = np.ascontiguousarray(cons_unions, dtype=np.float64)
+    A, N, C = ci.shape
     # running sums start from attack 0, accumulated image by image in float32 (:236-246)
-    run_i = np.add.accumulate(ci[0].astype(np.float32), axis=0)[-1].astype(np.float64)
-    run_u = np.add.accumulate(cu[0].astype(np.float32), axis=0)[-1].astype(np.float64)
-    final = _compute_miou(run_i, run_u)
-    sel = [0] * N
+    run_i = np.ascontiguousarray(np.add.accumulate(ci[0].astype(np.float32), axis=0)[-1].astype(np.float64))
+    run_u = np.ascontiguousarray(np.add.accumulate(cu[0].astype(np.float32), axis=0)[-1].astype(np.float64))
+    final = np.array([_compute_miou(run_i, run_u)], dtype=np.float64)
+    sel = np.zeros(N, dtype=np.int32)
     prev_best = 10
     for _ in range(n_rounds):
         order = list(range(0, N))
         rng.shuffle(order)
-        for idx in order:
-            for a in range(A):
-                ri, ru = _f32(run_i), _f32(run_u)       # torch.tensor(list) -> float32 (:311-312)
-                new_i = ri + (ci[a, idx] - ci[sel[idx], idx])
-                new_u = ru + (cu[a, idx] - cu[sel[idx], idx])
-                keep = ru != 0
-                est = exact_mean(new_i[keep] / (new_u[keep] + 1e-8))
-                if est < final:
-                    sel[idx] = a
-                    run_i, run_u = new_i, new_u
-            final = _compute_miou(_f32(run_i), _f32(run_u))
-        if prev_best - final <= 1e-6:
+        order = np.asarray(order, dtype=np.int32)
+        _lib.check(lib.robseg_sea_greedy_round_host(_dptr(ci), _dptr(cu), A, N, C, _dptr(order), _dptr(sel),
+                                                    _dptr(run_i), _dptr(run_u), _dptr(final)),
+                   "robseg_sea_greedy_round_host")
+        if prev_best - final[0] <= 1e-6:
             break
-        prev_best = final
-    return final, sel
+        prev_best = float(final[0])
+    return float(final[0]), [int(a) for a in sel]
 
 
 class evalSEA:

@@ -122,6 +122,38 @@ def test_exact_mean_matches_statistics_mean(mods):
         assert mods.worse.exact_mean(v) == statistics.mean(v.tolist())
 
 
+def test_exact_mean_hard_cases(mods):
+    """Cancellation, mixed signs and magnitudes, halfway cases: the C++ super-accumulator must agree
+    with statistics.mean (exact rational arithmetic) bit for bit."""
+    rng = np.random.default_rng(1)
+    cases = [[1e16, 1.0, -1e16], [0.1] * 10, [1.0, 1e-30, -1.0], [2.0 ** -1060, 2.0 ** -1061, 2.0 ** -1062],
+             [1.7976931348623157e308, 1.7976931348623157e308, -1.7976931348623157e308], [0.0, -0.0, 0.0],
+             [1.0 + 2.0 ** -52, 1.0, 1.0], [3.0, 3.0 + 2.0 ** -51], [-5.5, 2.25, 1e-300], [1 / 3, 1 / 7, 1 / 11] * 50]
+    for _ in range(200):
+        n = int(rng.integers(1, 300))
+        v = rng.standard_normal(n) * 10.0 ** rng.integers(-20, 20, n)
+        cases.append(v.tolist())
+    for v in cases:
+        assert mods.worse.exact_mean(v) == statistics.mean(v), v[:4]
+    with pytest.raises(ValueError):
+        mods.worse.exact_mean([])
+    with pytest.raises(RuntimeError):
+        mods.worse.exact_mean([1.0, float("inf")])
+
+
+def test_greedy_worst_miou_vs_oracle_larger_problem(mods):
+    rng = np.random.default_rng(11)
+    A, N, C = 3, 60, 13
+    tgt = rng.integers(1, 4000, (1, N, C))
+    inter = np.minimum(rng.integers(0, 4000, (A, N, C)), tgt)
+    union = tgt + rng.integers(0, 3000, (A, N, C))
+    r1, r2 = random.Random(225), random.Random(225)
+    f1, s1 = mods.worse.greedy_worst_miou(inter, union, rng=r1)
+    f2, s2 = O.sea_worst_miou(inter, union, rng=r2)
+    assert f1 == f2 and s1 == s2
+    assert r1.random() == r2.random()  # same number of shuffles drawn
+
+
 def test_greedy_worst_miou_bit_exact(mods, golden):
     g = golden("sea")
     random.seed(225)
