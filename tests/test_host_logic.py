@@ -102,6 +102,26 @@ def test_consumers_cpu_shapes_and_fast_flag_is_inert_on_cpu(mods):
         s(torch.rand(1, 3, 48, 48))
 
 
+def test_upsample_walk_kernel_ownership_bound():
+    """upsample_bwd_walk_kernel assigns every output to the cell of its first tap and keeps <= RMAX =
+    ceil(W/w)+1 outputs per cell and row in registers; the walk also assumes the owner never skips
+    a cell.  Both follow from ATen's source-index formula for any ratio >= 1: checked here in float32
+    (two-step rounding and the fused variant the device may use)."""
+    f32 = np.float32
+    for w in list(range(1, 40)) + [59, 119, 128, 237]:
+        for W in range(w, min(10 * w, 1200) + 1):
+            sx = f32(w) / f32(W)
+            X = np.arange(W, dtype=np.float32)
+            srcs = ((sx * (X + f32(0.5)) - f32(0.5)).astype(np.float32),
+                    (np.float64(sx) * (X.astype(np.float64) + 0.5) - 0.5).astype(np.float32))
+            for src in srcs:
+                own = np.where(src < 0, -1, np.minimum(src.astype(np.int64), w - 1))
+                d = np.diff(own)
+                assert d.min(initial=0) >= 0 and d.max(initial=0) <= 1, (w, W)
+                assert np.bincount(own + 1, minlength=w + 1).max() <= -(-W // w) + 1, (w, W)
+                assert own[-1] == w - 1
+
+
 def test_bench_helpers():
     import bench
 
