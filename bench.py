@@ -47,6 +47,13 @@ def parse():
     ap.add_argument("--variant", default=None, help="ConvNeXt T|S (upernet) or ViT S|B|L (segmenter)")
     ap.add_argument("--model", default="upernet", choices=["upernet", "segmenter"],
                     help="consumer: configs[1] UperNet-ConvNeXt (default) or configs[2] Segmenter-ViT")
+    ap.add_argument("--workload", default="sea", choices=["sea", "pirat"],
+                    help="sea: configs[1]/[2] SEA step (default); pirat: configs[3] PIR-AT training step under DDP")
+    ap.add_argument("--own-consumer", action="store_true",
+                    help="drive consumers.py's look-alike networks instead of the reference's model classes "
+                         "(default: the reference's classes from baseline/_ref when that copy travelled)")
+    ap.add_argument("--no-ref-on-gpu", action="store_true",
+                    help="skip the unmodified-reference-on-this-GPU comparator (config.reference_on_gpu, N=1 only)")
     ap.add_argument("--micro", action="store_true", help="config-5 kernel microbench instead of the SEA step")
     ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--micro-dtype", default="fp32", choices=["fp32", "bf16"])
@@ -63,7 +70,7 @@ def parse():
     ap.add_argument("--debug-stack", type=int, default=0, help="dump python stacks to stderr every N seconds")
     args = ap.parse_args()
     if args.variant is None:
-        args.variant = "T" if args.model == "upernet" else "S"
+        args.variant = ("S" if args.workload == "pirat" else "T") if args.model == "upernet" else "S"
     return args
 
 
@@ -170,6 +177,109 @@ def sea_step(mods, model, x, y, w, args, world, e2e_host=None):
     return worst, (gi, gt, gp), None
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def import_reference(mods):
+    """Make the copy of the reference under baseline/_ref importable (timm / autoattack stubs from
+    dropin.shim_missing_deps) WITHOUT installing the drop-in: `semseg.*` stays the reference's."""
+    if not os.path.isdir(os.path.join(REF_DIR, "semseg")):
+        return False
+    mods["dropin"].shim_missing_deps()
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    cwd = os.getcwd()
+    os.chdir(REF_DIR)
+    try:
+        import semseg  # noqa: F401
+    finally:
+        os.chdir(cwd)
+    return True
+
+
+def build_consumer(args, mods, dev, accelerated=True):
+    """The network around the hot path.  Default: the REFERENCE's own model class (unmodified copy under
+    baseline/_ref), random init, with its bilinear up-samplings routed to the robseg kernels by
+    dropin.accelerate.  Fallback / --own-consumer: consumers.py."""
+    import torch
+
+    mode = upsample_mode(args) if accelerated else False
+    if not args.own_consumer:
+        try:
+            if import_reference(mods):
+                dropin = mods["dropin"]
+                torch.manual_seed(0)
+                model = dropin.reference_model(args.model, args.variant, args.classes, args.size).to(dev).eval()
+                if mode == "all":
+                    dropin.accelerate(model, head=True)
+                elif mode:
+                    (dropin.fast_logit_upsample if args.model == "upernet" else dropin.fast_interpolate)(model)
+                return model, ("reference class semseg.models.%s (unmodified copy under baseline/_ref), random init"
+                               % type(model).__name__)
+        except Exception as e:
+            print(f"[bench] reference model unusable ({e!r}); using consumers.py", file=sys.stderr)
+    torch.manual_seed(0)
+    if args.model == "segmenter":
+        model = mods["consumers"].segmenter_vit(args.variant, args.classes, args.size, fast_upsample=bool(mode))
+    else:
+        model = mods["consumers"].upernet_convnext(args.variant, args.classes, fast_upsample=mode)
+    return model.to(dev).eval(), "consumers.py look-alike (%s), random init" % type(model).__name__
+
+
+def reference_on_gpu(args, mods, dev, x, y, w):
+    """The honest same-hardware comparator: the UNMODIFIED reference attacker (baseline/_ref
+    semseg/attacker.py, stock ATen op chains) driving the reference's own model (stock F.interpolate)
+    on this GPU, same SEA step, re-forward of every adversarial batch as tools/infer.py:82-90 does.
+    One warm-up step, one timed step."""
+    import torch
+
+    try:
+        if not import_reference(mods):
+            return {"unavailable": "baseline/_ref did not travel"}
+        import semseg.attacker as RA
+
+        if RA.__name__.startswith("robseg_b200"):
+            return {"unavailable": "drop-in is installed in this process"}
+        saved = (args.own_consumer,)
+        args.own_consumer = False
+        model, desc = build_consumer(args, mods, dev, accelerated=False)
+        args.own_consumer = saved[0]
+        for p in model.parameters():
+            p.requires_grad_(True)
+        w_cpu = w.cpu()  # tools/infer.py:297-301 hands the attack a CPU weight tensor
+        B = x.shape[0]
+
+        def step():
+            for loss in LOSSES:
+                x_adv, _, acc = RA.apgd_largereps(model, x.clone(), y, w_cpu, norm="Linf", eps=args.eps / 255.0,
+                                                  n_iter=args.n_iter, loss=loss, track_loss="ce-avg", use_rs=True,
+                                                  early_stop=True, num_classes=args.classes)
+                with torch.no_grad():
+                    model(x_adv).max(1)[1]
+
+        torch.cuda.reset_peak_memory_stats(dev)
+        torch.manual_seed(1234)
+        step()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.manual_seed(1234)
+        t0.record()
+        step()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        peak = torch.cuda.max_memory_allocated(dev) / 2**30
+        del model
+        torch.cuda.empty_cache()
+        return {"value": round(B * args.n_iter * len(LOSSES) / (ms / 1e3), 3), "unit": UNIT,
+                "ms_per_step": round(ms, 1), "peak_mem_GiB": round(peak, 1), "steps": 1, "warmup": 1,
+                "what": "unmodified reference semseg/attacker.py::apgd_largereps + " + desc +
+                        " with stock F.interpolate, same step incl. the re-forward of x_adv, this GPU"}
+    except Exception as e:  # a comparator must never take the bench down
+        torch.cuda.empty_cache()
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -181,7 +291,7 @@ def run_ours(args):
 
     mods = {k: import_module("robseg_b200." + v) for k, v in dict(
         attacker="semseg.attacker", ops="ops", dist="dist", lib="_lib", consumers="consumers",
-        worse="tools.worse_only", graphs="graphs").items()}
+        worse="tools.worse_only", graphs="graphs", dropin="dropin", val="semseg.val").items()}
     mods["lib"].load()  # fails loudly if the CUDA extension is missing
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -193,14 +303,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     if args.micro:
         return run_micro(args, mods, dev, rank, world)
+    if args.workload == "pirat":
+        return run_pirat(args, mods, dev, rank, world, local)
 
-    torch.manual_seed(0)
-    if args.model == "segmenter":
-        model = mods["consumers"].segmenter_vit(args.variant, args.classes, args.size,
-                                                fast_upsample=bool(upsample_mode(args))).to(dev).eval()
-    else:
-        model = mods["consumers"].upernet_convnext(args.variant, args.classes,
-                                                   fast_upsample=upsample_mode(args)).to(dev).eval()
+    model, consumer_desc = build_consumer(args, mods, dev)
     for p in model.parameters():
         p.requires_grad_(True)  # as in the reference: parameters keep requires_grad
     B, C, S = args.batch, args.classes, args.size
@@ -290,6 +396,7 @@ def run_ours(args):
             "model_bwd_per_step": len(LOSSES) * args.n_iter,
             "adversarial_argmax": "re-forward of x_adv (tools/infer.py:82-90)" if args.reforward else
             "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)",
+            "consumer_model": consumer_desc,
             "consumer": "stock PyTorch fp32 (cuDNN conv TF32 default, matmul fp32)" +
                         (", forward / input-gradient backward replayed as CUDA graphs" if args.graph else ""),
             "bilinear_upsample": {False: "F.interpolate (stock) everywhere",
@@ -315,8 +422,202 @@ def run_ours(args):
                      "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
                      "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
     }
+    if world == 1 and not args.no_ref_on_gpu:
+        del model, keep, keep_e2e
+        torch.cuda.empty_cache()
+        line["config"]["reference_on_gpu"] = reference_on_gpu(args, mods, dev, x, y, w)
+        r = line["config"]["reference_on_gpu"].get("value")
+        if r:
+            line["config"]["reference_on_gpu"]["ours_over_reference_same_gpu"] = round(value / r, 3)
+    if world == 1:
+        line["config"]["loss_kernel_c151"] = loss_kernel_probe(mods, dev, B, 151, S)
     if not args.no_cpu_baseline and world == 1 and args.model == "upernet":
         line["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def loss_kernel_probe(mods, dev, B, C, S, reps=5):
+    """Fused loss+dlogits launch alone at [B,C,S,S] fp32 (inputs 2 x B*C*S*S*4 bytes, far beyond L2):
+    median CUDA-event time over `reps` launches after 3 warm-ups -> GB/s against the measured peak.
+    Used for the class count the default step does not run (151 = the reference's ADE20K config,
+    configs/ade20k_convnext.yaml:14)."""
+    import torch
+
+    ops = mods["ops"]
+    g = torch.Generator(device=dev).manual_seed(7)
+    z = 3 * torch.randn(B, C, S, S, device=dev, generator=g)
+    y = torch.randint(0, C, (B, S, S), device=dev, generator=g)
+    y = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.5, z.argmax(1), y)
+    dbuf = torch.empty_like(z)
+    ts = []
+    for i in range(3 + reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.loss_fwd_bwd(z, y, "mask-ce-avg", None, dlogits_out=dbuf)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    ms = statistics.median(ts)
+    nbytes = 2 * z.numel() * 4 + 8 * y.numel()
+    peak = load_peaks()[0]
+    del z, y, dbuf
+    torch.cuda.empty_cache()
+    return {"shape": [B, C, S, S], "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1),
+            "frac": round(nbytes / ms / 1e6 / peak, 4), "bytes": nbytes}
+
+
+# ------------------------------------------------------------------------------ PIR-AT (configs[3])
+PIRAT_METRIC = "PIR-AT training images/sec (UperNet-ConvNeXt-S, 2-step PGD inner attack, DDP, 512x512)"
+
+
+def run_pirat(args, mods, dev, rank, world, local):
+    """BASELINE configs[3]: one PIR-AT training step per rank and step -- eval-mode 2-step PGD inner attack
+    (semseg/val.py:181-218 semantics, eps 4/255, alpha 1e-2, loss "pgd") through the fused loss / step
+    kernels, then the train-mode forward (main + 0.4 aux CE), backward and AdamW step -- on the
+    reference's UperNet-ConvNeXt-S under DistributedDataParallel(find_unused_parameters=True), as
+    tools/train_rob_seg.py:143-145,293-352 runs it.  Timed in three modes: the drop-in default
+    (loss.backward() semantics, SURVEY 9-Q7: every attack step also produces parameter gradients and a
+    DDP all-reduce), input_grad_only=True, and the unmodified reference attack on the same GPUs."""
+    import torch
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    B, C, S = args.batch, args.classes, args.size
+    model, consumer_desc = build_consumer(args, mods, dev)
+    model.train()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    n_param = sum(p.numel() for p in model.parameters())
+    net = DDP(model, device_ids=[local], find_unused_parameters=True) if world > 1 else model
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0.05)
+    g = torch.Generator().manual_seed(100 + rank)
+    hx = torch.rand(B, 3, S, S, generator=g).pin_memory()
+    hy = torch.randint(0, C, (B, S, S), generator=g).pin_memory()
+    x, y = hx.to(dev), hy.to(dev)
+    val = mods["val"]
+    n_attack = 2
+    attacks = {
+        "dropin": val.Pgd_Attack_1(epsilon=4 / 255, alpha=1e-2, num_iter=n_attack, los="pgd"),
+        "input_grad_only": val.Pgd_Attack_1(epsilon=4 / 255, alpha=1e-2, num_iter=n_attack, los="pgd",
+                                            input_grad_only=True),
+    }
+    if not args.no_ref_on_gpu:
+        try:
+            if import_reference(mods):
+                import semseg.val as RV
+
+                if not RV.Pgd_Attack_1.__module__.startswith("robseg_b200"):
+                    # Pgd_Attack(epsilon=...) raises TypeError in the reference (SURVEY 9-Q6); Pgd_Attack_1
+                    # matches the trainer's keywords and the scalar "pgd" loss
+                    attacks["reference_on_gpu"] = RV.Pgd_Attack_1(epsilon=4 / 255, alpha=1e-2, num_iter=n_attack,
+                                                                  los="pgd")
+        except Exception as e:
+            print(f"[bench] reference attack unusable ({e!r})", file=sys.stderr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(attack, e2e):
+        xi, yi = (hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)) if e2e else (x, y)
+        opt.zero_grad(set_to_none=True)
+        net.eval()
+        adv = attack.adv_attack(net, xi, yi)[0]  # tools/train_rob_seg.py:333-336
+        net.train()
+        loss, _ = net(adv, yi)
+        loss.backward()
+        opt.step()
+        return loss.item() if e2e else loss
+
+    def timed(attack, n, e2e=False):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            last = step(attack, e2e)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), last
+
+    res = {}
+    sampler = ClockSampler(local)
+    clocks = None
+    for name, attack in attacks.items():
+        for _ in range(args.warmup):
+            step(attack, False)
+        if name == "dropin":
+            if rank == 0:
+                sampler.start()
+            launches0 = mods["lib"].launches
+            mods["ops"].profile_start()
+            ms, last = timed(attack, args.steps)
+            prof = mods["ops"].profile_stop()
+            launches = mods["lib"].launches - launches0
+            ms_e2e, _ = timed(attack, args.steps, e2e=True)
+            clocks = sampler.stop() if rank == 0 else None
+            res[name] = ms
+            assert torch.isfinite(last).all()
+        else:
+            res[name], _ = timed(attack, args.steps)
+    # replicas must still agree after all those steps
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(torch.equal(allc[0], c) for c in allc), "DDP replicas diverged"
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    by = {}
+    for name, nbytes, t in prof:
+        d = by.setdefault(name, [0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += t
+        d[2] += 1
+    lg = by.get("loss_grad", [0, 1e-9, 1])
+    achieved = lg[0] / (lg[1] / 1e3) / 1e9
+    ips = lambda m: round(world * B * args.steps / (m / 1e3), 3)  # noqa: E731
+    line = {
+        "metric": PIRAT_METRIC, "value": ips(res["dropin"]), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(res["dropin"] / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"configs[3]: PIR-AT step, UperNet-ConvNeXt-{args.variant}_CVST random init, {C} classes, {S}x{S}, "
+                        f"batch {B} per GPU, {n_attack}-step PGD inner attack (Pgd_Attack_1 semantics, eps 4/255, alpha 1e-2, "
+                        "loss pgd) + train forward/backward + AdamW(lr 1e-4, wd 0.05), "
+                        + (f"DistributedDataParallel x{world} (find_unused_parameters=True)" if world > 1 else "single process"),
+            "consumer_model": consumer_desc,
+            "parallelism": f"dp{world} (stock DDP gradient all-reduce over NCCL; attack kernels are rank-local)",
+            "l2_note": "inputs larger than L2: logits/dlogits 2x%.2f GB per loss launch" % (B * C * S * S * 4 / 1e9),
+            "modes_images_per_s": {k: ips(v) for k, v in res.items()},
+            "modes_ms_per_step": {k: round(v / args.steps, 2) for k, v in res.items()},
+            "attack_time_allreduce_bytes_per_step": {
+                "dropin (loss.backward() semantics, SURVEY 9-Q7)": n_param * 4 * n_attack if world > 1 else 0,
+                "input_grad_only": 0, "training backward": n_param * 4 if world > 1 else 0},
+            "parameters": n_param,
+            "attack_side_ms_per_step": round(sum(v[1] for v in by.values()) / args.steps, 3),
+            "kernels_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in by.items()},
+        },
+        "clocks": clocks,
+        "e2e": {"value": ips(ms_e2e), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4 + B * S * S * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused CE loss+dlogits, C=%d)" % C,
+                     "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s",
+                     "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C),
+                     "peak_source": peaks[1], "launches_timed": lg[2],
+                     "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
+                     "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
+    }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -504,15 +805,16 @@ def run_micro(args, mods, dev, rank, world):
 
 
 # ------------------------------------------------------------------------------ CPU arms
-def _cpu_sample(args, loss, seed, prefer_reference=True):
-    """One bounded CPU sample of the same workload: apgd_largereps (n_iter=3 -> stages 0/0/3, each
-    stage still pays its initial forward+backward) on ONE 512x512 image, C classes, UperNet-
-    ConvNeXt-T on the host cores.  Returns (seconds, image_iterations, kind)."""
+def _cpu_sample(args, loss, seed, prefer_reference=True, n_iter=None):
+    """One bounded CPU sample of the same workload: apgd_largereps with the GPU arm's n_iter (10 ->
+    stages 3/3/4: 13 forwards + 10 backwards, the same model passes per counted image-iteration as
+    the GPU arm) on ONE 512x512 image, C classes, UperNet-ConvNeXt-T on the host cores.
+    Returns (seconds, image_iterations, kind)."""
     import numpy as np
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    C, S, n_iter, B = args.classes, args.size, 3, 1
+    C, S, n_iter, B = args.classes, args.size, n_iter or args.n_iter, 1
     x, y = make_batch(B, C, S, seed)
     w = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(1))
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
@@ -575,7 +877,8 @@ def cpu_baseline(args, budget_s=25.0):
             break
     return {"value": round(n / t, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "host_cpus": os.cpu_count(),
-            "sample": f"{i + 1} of the 3 SEA losses x apgd_largereps(n_iter=3 -> 0/0/3 + 3 stage inits) on 1 image "
+            "sample": f"{i + 1} of the 3 SEA losses x apgd_largereps(n_iter={args.n_iter} -> "
+                      f"{'/'.join(map(str, stage_iters(args.n_iter)))}, same schedule as the GPU arm) on 1 image "
                       f"{args.size}x{args.size}, {args.classes} classes, UperNet-ConvNeXt-T on host cores, {t:.1f} s"}
 
 
@@ -592,24 +895,86 @@ def run_reference(args):
     except AttributeError:
         n_thr = os.cpu_count() or 1
     torch.set_num_threads(max(1, n_thr))
-    for i in range(args.warmup):
-        _cpu_sample(args, LOSSES[i % 3], 50 + i)
+    if args.workload == "pirat":
+        return run_reference_pirat(args, rank, world)
+    for i in range(args.warmup):  # untimed: a short schedule is enough to touch every code path
+        _cpu_sample(args, LOSSES[i % 3], 50 + i, n_iter=3)
     t, n, kind = 0.0, 0, None
     for i in range(args.steps):
         dt, it, kind = _cpu_sample(args, LOSSES[i % 3], 100 + i)
         t += dt
         n += it
     value = n / t
-    sample = (f"each step = one SEA loss (rotating {LOSSES}) x apgd_largereps(n_iter=3 -> stages 0/0/3, 6 fwd + 5 bwd) "
+    st = stage_iters(args.n_iter)
+    sample = (f"each step = one SEA loss (rotating {LOSSES}) x apgd_largereps(n_iter={args.n_iter} -> stages "
+              f"{'/'.join(map(str, st))}, {args.n_iter + 3} fwd + {args.n_iter} bwd: the GPU arm's schedule) "
               f"on 1 image {args.size}x{args.size}, {args.classes} classes, UperNet-ConvNeXt-T, host cores")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / max(args.steps, 1) * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1] on the host CPU, bounded sample: {sample}"},
+        "config": {"workload": f"configs[1] on the host CPU, bounded sample: {sample}",
+                   "model_fwd_per_image_iteration": (args.n_iter + 3) / args.n_iter,
+                   "model_bwd_per_image_iteration": 1.0},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "host_cpus": os.cpu_count(), "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def run_reference_pirat(args, rank, world):
+    """configs[3] on the host CPU: the reference's own Pgd_Attack_1 (semseg/val.py:181-218) + train step on
+    ONE 512x512 image per step, UperNet-ConvNeXt-S, all host threads."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+
+    ref_shims.install()
+    sys.path.insert(0, REF_DIR)
+    cwd = os.getcwd()
+    os.chdir(REF_DIR)
+    try:
+        import semseg.val as RV
+        from semseg.models import UperNetForSemanticSegmentation
+    finally:
+        os.chdir(cwd)
+    C, S = args.classes, args.size
+    torch.manual_seed(0)
+    model = UperNetForSemanticSegmentation(f"ConvNeXt-{args.variant}_CVST", C, None)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.05)
+    attack = RV.Pgd_Attack_1(epsilon=4 / 255, alpha=1e-2, num_iter=2, los="pgd")
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # val.py:192 hard-codes .cuda()
+    g = torch.Generator().manual_seed(100)
+    t = 0.0
+    try:
+        for i in range(args.warmup + args.steps):
+            x, y = torch.rand(1, 3, S, S, generator=g), torch.randint(0, C, (1, S, S), generator=g)
+            t0 = time.time()
+            opt.zero_grad(set_to_none=True)
+            model.eval()
+            adv = attack.adv_attack(model, x, y)[0]
+            model.train()
+            loss, _ = model(adv, y)
+            loss.backward()
+            opt.step()
+            if i >= args.warmup:
+                t += time.time() - t0
+    finally:
+        torch.Tensor.cuda = real_cuda
+    value = args.steps / t
+    sample = (f"each step = the reference's Pgd_Attack_1 (2 steps, loss pgd) + train forward/backward + AdamW on 1 image "
+              f"{S}x{S}, {C} classes, UperNet-ConvNeXt-{args.variant}, host cores")
+    print(json.dumps({
+        "impl": "reference", "metric": PIRAT_METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / max(args.steps, 1) * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[3] on the host CPU, bounded sample: {sample}"},
+        "cpu_baseline": {"value": round(value, 4), "unit": "images/s", "cores": torch.get_num_threads(),
+                         "kind": "reference", "host_cpus": os.cpu_count(), "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 

@@ -1,40 +1,208 @@
-"""Swap the B200 modules into a checkout of the reference.
+"""Swap the B200 modules into a checkout of the reference and run ITS drivers on them.
 
     import robseg_b200.dropin as dropin        # (alias from __graft_entry__.load_package)
     dropin.install("/path/to/Robust-Segmentation")
     import tools.infer                         # now binds to the B200 attacker / evalSEA
+    ns = dropin.run_infer_main(["--cfg", "configs/ade20k_convnext.yaml", "--eps", "8"])
 
 ``install`` imports the reference's own ``semseg`` package (models, datasets, configs stay
 theirs), then rebinds exactly the names SURVEY.md section 8b lists: the ``semseg.attacker``
 module, ``semseg.val.{Pgd_Attack, Pgd_Attack_1, evaluate}``, ``semseg.metrics.Metrics``,
-``semseg.losses.{CrossEntropy, get_loss}`` and ``tools.worse_only.evalSEA``.
+``semseg.losses.{CrossEntropy, get_loss}``, ``tools.worse_only.evalSEA`` and -- so that the
+reference's own SEA driver gets the device-resident bookkeeping -- ``tools.infer.{attacker,
+evalSEA, evaluate, eval_performance, check_imgs}`` (tools/infer.py:16,22,39-155).
+``uninstall`` puts every original back.
+
+``run_infer_main`` executes the reference's ``tools/infer.py`` ``__main__`` block (:220-413)
+unmodified, inside the rebound ``tools.infer`` namespace.  ``runpy.run_module("tools.infer",
+run_name="__main__")`` would re-execute the module's ``def evaluate`` / ``def eval_performance``
+and shadow the rebinding, so only the main block is compiled from the file's own source.
 """
+import ast
 import importlib
 import sys
+import types
+
+_saved = []  # (container, key, had_it, old_value, is_sys_modules)
 
 
-def install(reference_root=None):
+def shim_missing_deps():
+    """Make a reference checkout importable where ``timm==0.6.5`` / ``autoattack`` (fra31/auto-attack
+    @a392200, requirements.txt:3,68) are not installed.  Only names the reference touches at import
+    time are provided: a print/append ``Logger`` and three norm helpers
+    (semseg/attacker.py:6), ``DropPath`` / ``trunc_normal_`` / ``register_model`` and a few ``None``
+    factories (semseg/models/*).  Packages that do import are left alone."""
+    import torch.nn as nn
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def importable(name):
+        if name in sys.modules:
+            return True
+        try:
+            importlib.import_module(name)
+            return True
+        except Exception:
+            return False
+
+    if not importable("autoattack.other_utils"):
+        def _flat(x):
+            return x.reshape(x.shape[0], -1)
+
+        def _keep(z, x, keepdim):
+            return z.view(-1, *[1] * (x.dim() - 1)) if keepdim else z
+
+        class Logger:
+            def __init__(self, log_path=None):
+                self.log_path = log_path
+
+            def log(self, str_to_log):
+                print(str_to_log)
+                if self.log_path is not None:
+                    with open(self.log_path, "a") as f:
+                        f.write(str_to_log + "\n")
+
+        ou = mod("autoattack.other_utils",
+                 L0_norm=lambda x: _flat(x != 0.0).sum(-1),
+                 L1_norm=lambda x, keepdim=False: _keep(_flat(x.abs()).sum(-1), x, keepdim),
+                 L2_norm=lambda x, keepdim=False: _keep(_flat(x ** 2).sum(-1).sqrt(), x, keepdim),
+                 Logger=Logger)
+        mod("autoattack", other_utils=ou)
+
+    if not importable("timm.models.layers"):
+        class DropPath(nn.Module):
+            def __init__(self, drop_prob=0.0):
+                super().__init__()
+                self.drop_prob = drop_prob
+
+            def forward(self, x):
+                if self.drop_prob == 0.0 or not self.training:
+                    return x
+                keep = 1.0 - self.drop_prob
+                mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+                return x * mask / keep
+
+        layers = mod("timm.models.layers", DropPath=DropPath, trunc_normal_=nn.init.trunc_normal_)
+        registry = mod("timm.models.registry", register_model=lambda fn: fn)
+        vit = mod("timm.models.vision_transformer", _create_vision_transformer=None, default_cfgs={},
+                  _load_weights=None)
+        models = mod("timm.models", layers=layers, registry=registry, vision_transformer=vit)
+        mod("timm", models=models, optim=mod("timm.optim", create_optimizer=None),
+            scheduler=mod("timm.scheduler", create_scheduler=None))
+
+
+def _rebind(container, key, value, is_modules=False):
+    if is_modules:
+        _saved.append((container, key, key in container, container.get(key), True))
+        container[key] = value
+    else:
+        _saved.append((container, key, hasattr(container, key), getattr(container, key, None), False))
+        setattr(container, key, value)
+
+
+def install(reference_root=None, shims=True, accelerate_models=False):
+    """Rebind the hot-path names of an importable reference checkout to the B200 modules.
+    Works whether or not ``tools.infer`` / ``tools.train_rob_seg`` were imported before.
+
+    ``accelerate_models=True`` also wraps the model factories the drivers call
+    (``UperNetForSemanticSegmentation``, ``create_segmenter``: tools/infer.py:256-264,
+    tools/train_rob_seg.py) so that every model they build has its bilinear up-samplings on the
+    robseg kernels (:func:`accelerate`).  The model classes themselves stay the
+    reference's."""
     from .semseg import attacker, losses, metrics, val
-    from .tools import worse_only
+    from .tools import infer, worse_only
 
+    if _saved:
+        uninstall()
+    if shims:
+        shim_missing_deps()
     if reference_root is not None and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     ref = importlib.import_module("semseg")
-    sys.modules["semseg.attacker"] = attacker
-    ref.attacker = attacker
+    _rebind(sys.modules, "semseg.attacker", attacker, is_modules=True)
+    _rebind(ref, "attacker", attacker)
     for modname, names, src in (
         ("semseg.val", ("Pgd_Attack", "Pgd_Attack_1", "evaluate"), val),
         ("semseg.metrics", ("Metrics",), metrics),
         ("semseg.losses", ("CrossEntropy", "get_loss"), losses),
         ("tools.worse_only", ("evalSEA",), worse_only),
+        ("tools.infer", ("evalSEA",), worse_only),
+        ("tools.infer", ("evaluate", "eval_performance", "check_imgs"), infer),
+        ("tools.train_rob_seg", ("Pgd_Attack", "evaluate"), val),
+        ("tools.train_rob_seg", ("get_loss",), losses),
     ):
+        if modname.startswith("tools.train") and modname not in sys.modules:
+            continue  # the trainer binds at import time: importing it after install() is enough
         try:
             m = importlib.import_module(modname)
         except Exception:  # optional pieces of the reference may not import (missing deps)
             continue
         for n in names:
-            setattr(m, n, getattr(src, n))
+            _rebind(m, n, getattr(src, n))
+    for modname in ("tools.infer", "tools.train_rob_seg"):
+        m = sys.modules.get(modname)
+        if m is not None and hasattr(m, "attacker"):
+            _rebind(m, "attacker", attacker)
+        if m is not None and accelerate_models:
+            for n in ("UperNetForSemanticSegmentation", "create_segmenter"):
+                if hasattr(m, n):
+                    _rebind(m, n, _accelerating(getattr(m, n)))
     return attacker
+
+
+def _accelerating(factory):
+    def build(*a, **k):
+        return accelerate(factory(*a, **k))
+
+    build.__name__ = getattr(factory, "__name__", "build")
+    build.__wrapped__ = factory
+    return build
+
+
+def uninstall():
+    """Undo ``install``: every rebound name gets the reference's own object back."""
+    while _saved:
+        container, key, had, old, is_modules = _saved.pop()
+        if is_modules:
+            if had:
+                container[key] = old
+            else:
+                container.pop(key, None)
+        elif had:
+            setattr(container, key, old)
+        else:
+            delattr(container, key)
+
+
+def run_infer_main(argv, overrides=None):
+    """Run the reference's SEA driver -- the ``if __name__ == "__main__":`` block of ITS
+    ``tools/infer.py`` (:220-413), compiled from the checkout's own source -- in the rebound
+    ``tools.infer`` namespace.  ``install()`` must have been called.  ``overrides`` are extra
+    names placed in that namespace first (tests swap ``get_data`` for a synthetic dataset).
+    Returns the namespace after the run (``clean_stats``, ``evall.saveDict``, ...)."""
+    if not _saved:
+        raise RuntimeError("dropin.install(reference_root) first")
+    mod = importlib.import_module("tools.infer")
+    with open(mod.__file__) as f:
+        tree = ast.parse(f.read(), mod.__file__)
+    main = [n for n in tree.body if isinstance(n, ast.If) and isinstance(n.test, ast.Compare)
+            and getattr(n.test.left, "id", None) == "__name__"]
+    if len(main) != 1:
+        raise RuntimeError(f"{mod.__file__}: expected exactly one __main__ block")
+    code = compile(ast.Module(body=main[0].body, type_ignores=[]), mod.__file__, "exec")
+    ns = dict(vars(mod))
+    ns.update(overrides or {})
+    old_argv = sys.argv
+    sys.argv = ["tools.infer"] + list(argv)
+    try:
+        exec(code, ns)
+    finally:
+        sys.argv = old_argv
+    return ns
 
 
 def fast_logit_upsample(model, head=False):
@@ -50,8 +218,6 @@ def fast_logit_upsample(model, head=False):
     ``nn.functional.interpolate`` by name: that name is rebound to ``ops.interpolate`` for the
     duration of the head's forward only (other modes / dtypes / devices fall through to the
     stock function)."""
-    import types
-
     from . import ops
 
     if not (hasattr(model, "backbone") and hasattr(model, "decode_head")):
@@ -71,3 +237,55 @@ def fast_logit_upsample(model, head=False):
 
     model.forward = types.MethodType(forward, model)
     return model
+
+
+def fast_interpolate(model):
+    """Any other reference model (``SegMenter``: semseg/models/segmenter.py:193-231, x16 bilinear
+    up-sampling of the class masks at :228; ``PSPNet``): its ``F.interpolate`` calls resolve
+    ``torch.nn.functional.interpolate`` at call time, so the whole eval-mode forward runs with that
+    name rebound to ``ops.interpolate`` (bilinear / align_corners=False / fp32 / CUDA -> robseg
+    kernels, everything else -> the stock function)."""
+    from . import ops
+
+    stock_forward = model.forward
+
+    def forward(self, *a, **k):
+        if self.training:
+            return stock_forward(*a, **k)
+        with ops.patched_interpolate():
+            return stock_forward(*a, **k)
+
+    model.forward = types.MethodType(forward, model)
+    return model
+
+
+def accelerate(model, head=True):
+    """``fast_logit_upsample`` for UperNet-shaped models, ``fast_interpolate`` otherwise."""
+    if hasattr(model, "backbone") and hasattr(model, "decode_head"):
+        return fast_logit_upsample(model, head=head)
+    return fast_interpolate(model)
+
+
+def reference_model(kind, variant, n_cls, image_size=512):
+    """Random-init instance of one of the REFERENCE's model classes (the checkout must be importable:
+    ``install`` / ``shim_missing_deps`` + sys.path).  ``kind="upernet"``:
+    ``UperNetForSemanticSegmentation(f"ConvNeXt-{variant}_CVST", n_cls, None)`` (tools/infer.py:262);
+    ``kind="segmenter"``: ``SegMenter`` over ``VisionTransformer`` + ``MaskTransformer`` built
+    directly with the arguments ``load_config_segmenter`` / ``create_vit`` / ``create_decoder`` derive
+    for ``vit_{small,base,large}_patch16`` (semseg/utils/utils.py:258-277, semseg/models/segmenter.py:
+    265-342), because ``create_vit`` insists on a checkpoint file (:299)."""
+    if kind == "upernet":
+        from semseg.models import UperNetForSemanticSegmentation
+
+        return UperNetForSemanticSegmentation(f"ConvNeXt-{variant}_CVST", n_cls, None)
+    if kind != "segmenter":
+        raise ValueError(kind)
+    from semseg.models.segmenter import MaskTransformer, SegMenter, VisionTransformer
+
+    name, d, heads, layers = {"S": ("vit_small_patch16_224", 384, 6, 12), "B": ("vit_base_patch16_384", 768, 12, 12),
+                              "L": ("vit_large_patch16_384", 1024, 16, 24)}[variant]
+    enc = VisionTransformer(image_size=(image_size, image_size), patch_size=16, n_layers=layers, d_model=d,
+                            d_ff=4 * d, n_heads=heads, n_cls=1000, dropout=0.0, drop_path_rate=0.1, distilled=False)
+    dec = MaskTransformer(n_cls=n_cls, patch_size=16, d_encoder=d, n_layers=2, n_heads=d // 64, d_model=d,
+                          d_ff=4 * d, drop_path_rate=0.0, dropout=0.1)
+    return SegMenter(enc, dec, n_cls=n_cls, backbone=name)

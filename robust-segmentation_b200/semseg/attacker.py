@@ -227,6 +227,8 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
             x_in = x_in_buf.detach().requires_grad_(need_grad)
             with torch.set_grad_enabled(need_grad):
                 logits = model(x_in)
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()  # fp16 under autocast: F.cross_entropy up-casts too (attacker.py:147)
         out = ops.loss_fwd_bwd(logits, y, loss, w_dev, want_grad=need_grad, want_pred=keep_pred,
                                dlogits_out=dbuf)
         g = None

@@ -71,6 +71,8 @@ class _PgdBase:
         for _ in range(self.num_iter):
             xin = x_in.detach().requires_grad_(True)
             logits = model(xin)
+            if logits.dtype not in (torch.float32, torch.bfloat16):
+                logits = logits.float()  # fp16 under autocast(AMP): F.cross_entropy up-casts too
             out = ops.loss_fwd_bwd(logits, y, self.los_name, None, grad_scale=gscale,
                                    want_grad=True, ignore_index=ignore, dlogits_out=dbuf)
             dbuf = out.dlogits

@@ -13,9 +13,30 @@ batch to the CPU (:151, 50 MB per batch at B=16), later moves it back and re-for
   mAcc / aAcc / mIoU replay the reference's float32 finaliser.  The returned ``l_output`` is
   the ``[N,H,W]`` int64 argmax store with -1 at ignored pixels, as ``evalSEA`` expects.
 """
+import functools
+
 import torch
 
 from .. import ops
+from ..semseg import attacker as _attacker
+
+
+class AdvLoader(list):
+    """What ``evaluate`` returns: the reference's list of ``(x_adv, target)`` pairs, plus -- when the
+    attack is this package's ``apgd_largereps`` -- the argmax map of every adversarial batch as
+    the attack saw it (``return_pred``) and the device copy of its targets.
+    ``eval_performance(model, adv_loader)`` then needs neither the H2D copy of ``x_adv`` nor the
+    re-forward of tools/infer.py:82-84; the pairs themselves stay as the reference defines them."""
+
+    def __init__(self, model=None):
+        super().__init__()
+        self.model = model
+        self.device_items = []  # per batch (pred [B,H,W] int64, target [B,H,W]) on the device
+
+
+def _returns_pred(attack_fn):
+    f = attack_fn.func if isinstance(attack_fn, functools.partial) else attack_fn
+    return f is _attacker.apgd_largereps
 
 
 def check_imgs(adv, x, norm, verbose=False):
@@ -39,14 +60,21 @@ def eval_performance(model, data_loader, n_batches=-1, n_cls=21, return_output=F
     inter = torch.zeros(n_cls, dtype=torch.int64, device=dev)
     tgt, prd = torch.zeros_like(inter), torch.zeros_like(inter)
     l_output = []
+    cached = None
+    if isinstance(data_loader, AdvLoader) and data_loader.model is model and \
+            len(data_loader.device_items) == len(data_loader):
+        cached = data_loader.device_items
     for i, vals in enumerate(data_loader):
-        input, target = vals[0].to(dev, non_blocking=True), vals[1].to(dev, non_blocking=True)
-        with torch.no_grad():
-            output = model(input)
-        if output.dtype not in (torch.float32, torch.bfloat16):
-            output = output.float()
-        pred = ops.loss_fwd_bwd(output, target, "argmax", want_grad=False, want_pred=True,
-                                ignore_index=ignore_index, want_stats=False).pred
+        if cached is not None:  # argmax maps handed over by the attack: no re-forward (8f-2)
+            pred, target = cached[i][0].clone(), cached[i][1]
+        else:
+            input, target = vals[0].to(dev, non_blocking=True), vals[1].to(dev, non_blocking=True)
+            with torch.no_grad():
+                output = model(input)
+            if output.dtype not in (torch.float32, torch.bfloat16):
+                output = output.float()
+            pred = ops.loss_fwd_bwd(output, target, "argmax", want_grad=False, want_pred=True,
+                                    ignore_index=ignore_index, want_stats=False).pred
         pred[target == ignore_index] = ignore_index  # :90
         c = ops.pixel_hist(pred, target, n_cls, ignore_index)
         inter += c["inter"].sum(0)
@@ -81,11 +109,16 @@ def evaluate(val_loader, model, attack_fn, n_batches=-1, args=None, weights=None
     "loader": a list of ``(x_adv, target)`` pairs (CPU tensors unless keep_on_device)."""
     model.eval()
     dev = torch.device(device)
-    adv_loader, pending = [], None
+    adv_loader, pending = AdvLoader(model), None
+    with_pred = _returns_pred(attack_fn)
     for i, (input, target, _) in enumerate(val_loader):
         input = input.to(dev, non_blocking=True)
         target = target.to(dev, non_blocking=True)
-        x_adv, _, acc = attack_fn(model, input.clone(), target, weights)
+        if with_pred:
+            x_adv, _, acc, pred = attack_fn(model, input.clone(), target, weights, return_pred=True)
+            adv_loader.device_items.append((pred, target))
+        else:
+            x_adv, _, acc = attack_fn(model, input.clone(), target, weights)
         if args is not None and getattr(args, "norm", None):
             check_imgs(input, x_adv, norm=args.norm)
         if keep_on_device:

@@ -26,6 +26,48 @@ from .worse_only import SEED, greedy_worst_miou
 LOSSES = ("mask-ce-bal", "mask-ce-avg", "js-avg")
 
 
+def _own_batches(loader, rank, world, n_batches):
+    """(sizes of ALL batches, index of this rank's first batch, iterable over this rank's batches only).
+
+    A rank must not decode or hold batches it does not attack (ADE20K val at 512^2 is ~6 GB of
+    host memory per copy).  For a sequential ``DataLoader`` the batch sizes follow from
+    ``len(dataset)`` and the rank iterates a ``Subset`` of its own images; for any other sized
+    iterable the foreign batches are skipped while iterating and only their sizes are kept."""
+    import torch.utils.data as tud
+
+    def limit(nb):
+        return nb if n_batches is None or n_batches < 0 else min(nb, n_batches)
+
+    if isinstance(loader, tud.DataLoader) and loader.batch_size and \
+            isinstance(loader.sampler, tud.SequentialSampler):
+        n, bs = len(loader.dataset), loader.batch_size
+        nb = limit(n // bs if loader.drop_last else -(-n // bs))
+        sizes = [min(bs, n - i * bs) for i in range(nb)]
+        lo_b, hi_b = rdist.shard_range(nb, rank, world)
+        if world == 1:
+            own = (v for i, v in enumerate(loader) if i < nb)
+        else:
+            sub = tud.Subset(loader.dataset, range(lo_b * bs, min(hi_b * bs, n, sum(sizes))))
+            own = tud.DataLoader(sub, batch_size=bs, shuffle=False, num_workers=loader.num_workers,
+                                 collate_fn=loader.collate_fn, pin_memory=loader.pin_memory,
+                                 worker_init_fn=loader.worker_init_fn) if hi_b > lo_b else []
+        return sizes, lo_b, own
+    if hasattr(loader, "__len__"):
+        nb = limit(len(loader))
+        lo_b, hi_b = rdist.shard_range(nb, rank, world)
+        sizes, mine = [], []
+        for i, vals in enumerate(loader):
+            if i >= nb:
+                break
+            sizes.append(vals[0].shape[0])
+            if lo_b <= i < hi_b:
+                mine.append((vals[0], vals[1]))
+        return sizes, lo_b, mine
+    batches = [(v[0], v[1]) for i, v in enumerate(loader) if n_batches is None or n_batches < 0 or i < n_batches]
+    lo_b, hi_b = rdist.shard_range(len(batches), rank, world)
+    return [b[0].shape[0] for b in batches], lo_b, batches[lo_b:hi_b]
+
+
 def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, losses=LOSSES,
             n_batches=-1, device="cuda", keep_adv=False, group=None, shard=True, seed=None):
     """Returns a dict: ``clean`` and per-loss ``{mAcc,aAcc,mIoU}``, ``worst_Acc``,
@@ -38,20 +80,15 @@ def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, los
     dev = torch.device(device)
     world = dist.get_world_size(group) if shard and dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    batches = []
-    for i, vals in enumerate(loader):
-        batches.append((vals[0], vals[1]))
-        if i + 1 == n_batches:
-            break
-    sizes = [b[0].shape[0] for b in batches]
+    sizes, lo_b, own = _own_batches(loader, rank, world, n_batches)
     n_total = sum(sizes)
-    lo_b, hi_b = rdist.shard_range(len(batches), rank, world)
     img_lo = sum(sizes[:lo_b])
     A = len(losses)
     per_loss = [[] for _ in range(A)]   # per batch [3, B, C] counters for every attack
     clean_cnt = []
     advs = [[] for _ in range(A)]
-    for bi, (x, y) in enumerate(batches[lo_b:hi_b], start=lo_b):
+    for bi, vals in enumerate(own, start=lo_b):
+        x, y = vals[0], vals[1]
         if seed is not None:
             torch.manual_seed(seed + bi)
         x = x.to(dev, non_blocking=True)

@@ -133,28 +133,29 @@ class evalSEA:
         return torch.cat(out)[:n_max]
 
     def per_image_counts(self, n_images=None):
-        """Exact int64 (inter, tgt, prd) of shape [A,N,C], computed once on the device."""
-        if self._counts is not None and (n_images is None or self._counts[0].shape[1] == n_images):
+        """Exact int64 (inter, tgt, prd) of shape [A,N,C], computed once on the device over ALL
+        stored predictions; ``n_images`` returns the leading slice (``worse_case_eval(bs, n_batches)``),
+        so a truncated request never shortens what ``worst_case_miou`` sees afterwards."""
+        if self._counts is None:
+            preds = self._load_outputs()
+            A, N = preds.shape[:2]
+            target = self._targets(N)
+            N = min(N, target.shape[0])
+            inter = torch.zeros((A, N, self.n_cls), dtype=torch.int64, device=self.device)
+            tgt, prd = torch.zeros_like(inter), torch.zeros_like(inter)
+            chunk = max(1, (1 << 28) // max(1, preds[0, 0].numel() * 8 * A))  # ~256 MB of preds per launch
+            for s in range(0, N, chunk):
+                e = min(N, s + chunk)
+                p = preds[:, s:e].to(self.device, non_blocking=True).reshape(A * (e - s), -1)
+                t = target[s:e].to(self.device, non_blocking=True).reshape(e - s, -1)
+                c = ops.pixel_hist(p, t, self.n_cls, -1)
+                inter[:, s:e] = c["inter"].view(A, e - s, -1)
+                tgt[:, s:e] = c["tgt"].view(A, e - s, -1)
+                prd[:, s:e] = c["prd"].view(A, e - s, -1)
+            self._counts = (inter, tgt, prd)
+        if n_images is None or n_images >= self._counts[0].shape[1]:
             return self._counts
-        preds = self._load_outputs()
-        A, N = preds.shape[:2]
-        if n_images is not None:
-            N = min(N, n_images)
-        target = self._targets(N)
-        N = min(N, target.shape[0])
-        inter = torch.zeros((A, N, self.n_cls), dtype=torch.int64, device=self.device)
-        tgt, prd = torch.zeros_like(inter), torch.zeros_like(inter)
-        chunk = max(1, (1 << 28) // max(1, preds[0, 0].numel() * 8 * A))  # ~256 MB of preds per launch
-        for s in range(0, N, chunk):
-            e = min(N, s + chunk)
-            p = preds[:, s:e].to(self.device, non_blocking=True).reshape(A * (e - s), -1)
-            t = target[s:e].to(self.device, non_blocking=True).reshape(e - s, -1)
-            c = ops.pixel_hist(p, t, self.n_cls, -1)
-            inter[:, s:e] = c["inter"].view(A, e - s, -1)
-            tgt[:, s:e] = c["tgt"].view(A, e - s, -1)
-            prd[:, s:e] = c["prd"].view(A, e - s, -1)
-        self._counts = (inter, tgt, prd)
-        return self._counts
+        return tuple(c[:, :n_images].contiguous() for c in self._counts)
 
     def worse_case_eval(self, bs=16, n_batches=-1):
         """Worst aACC across the three attacks, image-wise (:351-422)."""

@@ -301,3 +301,80 @@ def test_dropin_rebinds_reference_names(mods, tmp_path, monkeypatch):
     assert ref_sea.evalSEA is mods.worse.evalSEA
     for name in [n for n in sys.modules if n == "semseg" or n.startswith("semseg.") or n == "tools" or n.startswith("tools.")]:
         monkeypatch.delitem(sys.modules, name)
+
+
+def _purge_reference_modules(monkeypatch):
+    for name in [n for n in sys.modules if n == "semseg" or n.startswith("semseg.") or n == "tools" or n.startswith("tools.")]:
+        monkeypatch.delitem(sys.modules, name)
+
+
+def test_dropin_on_the_real_reference_copy(mods, monkeypatch):
+    """dropin.install / uninstall / run_infer_main against the unmodified copy of the reference under
+    baseline/_ref (no compute: import-level behaviour only).  tools.infer's own evaluate /
+    eval_performance / attacker / evalSEA are rebound and restored; run_infer_main really executes the
+    file's __main__ block (argparse sees --help and exits)."""
+    from importlib import import_module
+
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "semseg")):
+        pytest.skip("baseline/_ref not present")
+    _purge_reference_modules(monkeypatch)
+    monkeypatch.syspath_prepend(ref)
+    dropin = import_module("robseg_b200.dropin")
+    dropin.uninstall()
+    dropin.shim_missing_deps()
+    import tools.infer as TI
+
+    theirs = {n: getattr(TI, n) for n in ("attacker", "evaluate", "eval_performance", "evalSEA", "check_imgs")}
+    assert not theirs["attacker"].__name__.startswith("robseg_b200")
+    try:
+        dropin.install(ref, accelerate_models=True)
+        infer = import_module("robseg_b200.tools.infer")
+        assert TI.attacker is mods.attacker and sys.modules["semseg.attacker"] is mods.attacker
+        assert TI.evaluate is infer.evaluate and TI.eval_performance is infer.eval_performance
+        assert TI.evalSEA is mods.worse.evalSEA
+        assert TI.UperNetForSemanticSegmentation.__wrapped__.__name__ == "UperNetForSemanticSegmentation"
+        assert import_module("semseg.val").Pgd_Attack is mods.val.Pgd_Attack
+        assert import_module("semseg.models").UperNetForSemanticSegmentation is TI.UperNetForSemanticSegmentation.__wrapped__
+        with pytest.raises(SystemExit):  # the reference's argparse, reached through ITS main block
+            dropin.run_infer_main(["--help"])
+    finally:
+        dropin.uninstall()
+    for n, v in theirs.items():
+        assert getattr(TI, n) is v, n
+    assert sys.modules["semseg.attacker"] is theirs["attacker"]
+    with pytest.raises(RuntimeError):
+        dropin.run_infer_main(["--help"])  # not installed any more
+    _purge_reference_modules(monkeypatch)
+
+
+def test_run_sea_shards_the_loader_without_touching_foreign_batches(pkg):
+    """a rank must only decode its own batches."""
+    from importlib import import_module
+
+    sea = import_module("robseg_b200.tools.sea")
+
+    class Data(torch.utils.data.Dataset):
+        def __init__(self):
+            self.touched = []
+
+        def __len__(self):
+            return 10
+
+        def __getitem__(self, i):
+            self.touched.append(i)
+            return torch.full((3, 2, 2), float(i)), torch.zeros(2, 2, dtype=torch.int64), f"n{i}"
+
+    for rank, want_imgs, want_lo in ((0, list(range(0, 6)), 0), (1, list(range(6, 10)), 2)):
+        d = Data()
+        loader = torch.utils.data.DataLoader(d, batch_size=3, shuffle=False)
+        sizes, lo_b, own = sea._own_batches(loader, rank, 2, -1)
+        got = [int(v[0][k, 0, 0, 0]) for v in own for k in range(v[0].shape[0])]
+        assert sizes == [3, 3, 3, 1] and lo_b == want_lo and got == want_imgs and sorted(d.touched) == want_imgs
+    # n_batches cap and a plain list of batches
+    d = Data()
+    sizes, lo_b, own = sea._own_batches(torch.utils.data.DataLoader(d, batch_size=3), 0, 1, 2)
+    assert sizes == [3, 3] and len(list(own)) == 2
+    batches = [(torch.zeros(2, 3, 2, 2), torch.zeros(2, 2, 2)) for _ in range(5)]
+    sizes, lo_b, own = sea._own_batches(batches, 1, 2, -1)
+    assert sizes == [2] * 5 and lo_b == 3 and len(own) == 2

@@ -179,6 +179,32 @@ def test_sea_aggregation_matches_reference(golden):
     assert final == float(g["final_miou"])  # bit-exact python double
 
 
+def test_config1_full_size_aggregation_matches_reference(golden):
+    """BASELINE config 1 at full size (2 x 512^2, 21 classes): the reference's own tools/infer.py flow
+    (tests/golden/make_golden_config1.py) produced these argmax maps, per-attack statistics, worst-case
+    aACC and worst-case mIoU; the oracle's counters / finalisers / greedy must reproduce them exactly."""
+    g = golden("config1_sea")
+    C = 21
+    l_outs, y = g["l_outs"].astype(np.int64), g["y"].astype(np.int64)
+    A, N = l_outs.shape[:2]
+    cnt = O.pixel_hist(l_outs.reshape(A * N, -1), np.tile(y.reshape(N, -1), (A, 1)), C)
+    inter, tgt, prd = (cnt[k].reshape(A, N, C) for k in ("inter", "tgt", "prd"))
+    for a, k in enumerate(["mask-ce-bal", "mask-ce-avg", "js-avg"]):
+        m_acc, a_acc, m_iou = O.iou_acc_from_counts(inter[a].sum(0), tgt[a].sum(0), prd[a].sum(0))
+        # the class means are float32 sums in torch's reduction order; the oracle rounds the exact
+        # mean once -> equal to within one float32 ulp; the ratio of totals (aAcc) is exact
+        np.testing.assert_allclose([float(m_acc), float(a_acc), float(m_iou)], g["stats__" + k], rtol=1.5e-7)
+        assert float(a_acc) == g["stats__" + k][1], k
+        # per-image accuracy returned by the attack == accuracy of the re-forwarded argmax map
+        np.testing.assert_allclose(inter[a].sum(-1) / tgt[a].sum(-1), g["acc__" + k], atol=2e-5)
+    worst, per_attack = O.sea_worst_acc(O.sea_image_acc(inter, tgt))
+    assert worst == float(g["worst_Acc"])
+    assert np.array_equal(np.asarray(per_attack, dtype=np.float32), g["worst_Acc_indiv"])
+    random.seed(225)
+    final, _ = O.sea_worst_miou(inter, tgt + prd - inter)
+    assert final == float(g["final_miou"])
+
+
 @pytest.mark.parametrize("tag,kind,rs,clamp,best", [
     ("pgd1_pgd", "pgd", True, False, False),
     ("pgd_maskce", "mask-ce-avg", False, True, True),
