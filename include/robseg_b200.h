@@ -93,6 +93,26 @@ int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t* labels,
                         void* workspace, size_t workspace_bytes, robseg_stream_t stream);
 
 /*
+ * The same fused loss taken THROUGH the consumer's final bilinear up-sampling (SURVEY.md section 8f
+ * rank 1): logits = interpolate(low, size=(H,W), mode="bilinear", align_corners=False) as in
+ * semseg/models/uperforseg.py:416-418 (H = 4h) and semseg/models/segmenter.py:228 (H = 16h), followed by
+ * everything robseg_loss_fwd_bwd computes -- without ever materialising the [B,C,H,W] logits or their
+ * gradient.  The kernel interpolates on the fly from the low-resolution tensor and returns
+ *   dlow [B,C,h,w] = (d interpolate / d low)^T dlogits      (deterministic gather, no atomics)
+ * so the caller continues with autograd.grad(low, x, grad_outputs=dlow).
+ *  low [B,C,h,w] f32; labels [B,H,W] int64; H = R*h, W = R*w with R in {2,4,8,16};
+ *  dlow may be NULL (loss / argmax only); pred [B,H,W] int64 or NULL; the per-image outputs as above.
+ *  workspace: robseg_loss_upsampled_workspace_bytes(...) bytes, 16-byte aligned.
+ */
+size_t robseg_loss_upsampled_workspace_bytes(int B, int C, int h, int w, int H, int W);
+int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* labels, const float* class_w,
+                                  int loss_kind, int ignore_index, int B, int C, int h, int w, int H,
+                                  int W, const float* grad_scale, float* dlow, int64_t* pred,
+                                  float* loss_img, float* track_img, int32_t* correct_img,
+                                  int32_t* valid_img, void* workspace, size_t workspace_bytes,
+                                  robseg_stream_t stream);
+
+/*
  * One L-inf APGD update for the whole batch, bit-exact with the fp32 op chain of
  * semseg/attacker.py:388-410:
  *   g2 = x_adv - x_old
@@ -104,6 +124,20 @@ int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t* labels,
 int robseg_apgd_step(const float* x, const float* x_adv, const float* x_old, const float* grad,
                      const float* step, float eps, float a, float one_minus_a, int B,
                      int64_t n_per_img, float* x_new, robseg_stream_t stream);
+
+/*
+ * robseg_apgd_step with the PREVIOUS iteration's boolean-index row copies folded in
+ * (semseg/attacker.py:494-495 x_best_adv[ind_pred] = x_adv; :523-525 x_best[ind] = x_adv, grad_best[ind] =
+ * grad; :546-548 x_adv[fl] = x_best[fl], grad[fl] = grad_best[fl]), driven by the [3,B] flags
+ * robseg_apgd_bookkeep wrote: the step reads x_adv and grad anyway, so selected rows are stored from
+ * registers and restarted rows read x_best / grad_best instead (and are written back to x_adv / grad,
+ * in place).  Same arithmetic as robseg_apgd_step.  After the LAST iteration the caller flushes the
+ * pending copies with robseg_row_select.
+ */
+int robseg_apgd_step_fused(const float* x, float* x_adv, const float* x_old, float* grad,
+                           const float* step, float eps, float a, float one_minus_a, int B,
+                           int64_t n_per_img, float* x_new, const int32_t* flags, float* x_best_adv,
+                           float* x_best, float* grad_best, robseg_stream_t stream);
 
 /*
  * z <- clip01(x + clip(z - x, -eps, eps)): the stage hand-off of apgd_largereps

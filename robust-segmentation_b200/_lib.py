@@ -29,7 +29,11 @@ SIGNATURES = {
     "robseg_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i]),
     "robseg_loss_fwd_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _sz, _p]),
+    "robseg_loss_upsampled_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "robseg_loss_upsampled_fwd_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p,
+                                           _p, _p, _sz, _p]),
     "robseg_apgd_step": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p]),
+    "robseg_apgd_step_fused": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p, _p, _p, _p, _p]),
     "robseg_project_linf": (_i, [_p, _p, _p, _f, _i64, _p, _p]),
     "robseg_pgd_step": (_i, [_p, _p, _p, _f, _f, _i, _i, _i64, _p, _p]),
     "robseg_apgd_bookkeep": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i,

@@ -58,6 +58,65 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same update with the PREVIOUS iteration's flag-driven row copies folded in (semseg/attacker.py:
+// 494-495, 523-525, 546-548): the step reads x_adv and grad anyway, so the rows selected by the
+// bookkeeping kernel are stored to x_best_adv / x_best / grad_best from the registers that hold them,
+// and restarted rows take x_best / grad_best as their x_adv / grad (written back: x_adv becomes x_old).
+// Replaces two row_select launches per iteration whose source rows this kernel re-read one launch later.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+    apgd_step_fused_kernel(const float* __restrict__ x, float* xa_io, const float* __restrict__ xo,
+                           float* g_io, const float* __restrict__ step, float eps, float a, float oma,
+                           int B, int64_t n_per_img, float* __restrict__ out,
+                           const int32_t* __restrict__ flags, float* x_best_adv, float* x_best,
+                           float* grad_best) {
+  const int b = blockIdx.y;
+  const float st = __ldg(step + b);
+  const bool f_adv = __ldg(flags + b) != 0, f_best = __ldg(flags + B + b) != 0;
+  const bool f_restart = __ldg(flags + 2 * B + b) != 0 && !f_best;
+  const int64_t base = (int64_t)b * n_per_img;
+  if constexpr (VEC4) {
+    const int64_t n4 = n_per_img >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    float4* a4 = reinterpret_cast<float4*>(xa_io + base);
+    const float4* o4 = reinterpret_cast<const float4*>(xo + base);
+    float4* g4 = reinterpret_cast<float4*>(g_io + base);
+    float4* r4 = reinterpret_cast<float4*>(out + base);
+    float4* ba4 = reinterpret_cast<float4*>(x_best_adv + base);
+    float4* bx4 = reinterpret_cast<float4*>(x_best + base);
+    float4* bg4 = reinterpret_cast<float4*>(grad_best + base);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 vx = __ldcs(x4 + i), vo = __ldcs(o4 + i);
+      float4 va = a4[i], vg = g4[i];
+      if (f_adv) ba4[i] = va;
+      if (f_best) bx4[i] = va, bg4[i] = vg;
+      if (f_restart) {
+        va = bx4[i], vg = bg4[i];
+        a4[i] = va, g4[i] = vg;
+      }
+      float4 r;
+      r.x = apgd_elem(vx.x, va.x, vo.x, vg.x, st, eps, a, oma);
+      r.y = apgd_elem(vx.y, va.y, vo.y, vg.y, st, eps, a, oma);
+      r.z = apgd_elem(vx.z, va.z, vo.z, vg.z, st, eps, a, oma);
+      r.w = apgd_elem(vx.w, va.w, vo.w, vg.w, st, eps, a, oma);
+      r4[i] = r;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      float va = xa_io[base + i], vg = g_io[base + i];
+      if (f_adv) x_best_adv[base + i] = va;
+      if (f_best) x_best[base + i] = va, grad_best[base + i] = vg;
+      if (f_restart) {
+        va = x_best[base + i], vg = grad_best[base + i];
+        xa_io[base + i] = va, g_io[base + i] = vg;
+      }
+      out[base + i] = apgd_elem(x[base + i], va, xo[base + i], vg, st, eps, a, oma);
+    }
+  }
+}
+
 // out = clip01(x + clip(z-x, +-eps))   or, with noise, clip01(x + eps*noise)
 __global__ void __launch_bounds__(256)
     project_kernel(const float* __restrict__ z, const float* __restrict__ x,
@@ -226,6 +285,38 @@ extern "C" int robseg_apgd_step(const float* x, const float* x_adv, const float*
   else
     apgd_step_kernel<false><<<grid, 256, 0, stream>>>(x, x_adv, x_old, grad, step, eps, a,
                                                       one_minus_a, n_per_img, x_new);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int robseg_apgd_step_fused(const float* x, float* x_adv, const float* x_old, float* grad,
+                                      const float* step, float eps, float a, float one_minus_a, int B,
+                                      int64_t n_per_img, float* x_new, const int32_t* flags,
+                                      float* x_best_adv, float* x_best, float* grad_best,
+                                      robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(x && x_adv && x_old && grad && step && x_new && flags && x_best_adv && x_best && grad_best,
+                 "NULL pointer");
+  ROBSEG_REQUIRE(B > 0 && B <= 65535 && n_per_img > 0, "bad shape B=%d n=%lld", B, (long long)n_per_img);
+  ROBSEG_REQUIRE(x_new != x && x_new != x_adv && x_new != x_old && x_new != grad && x_new != x_best_adv &&
+                     x_new != x_best && x_new != grad_best,
+                 "x_new must not alias another buffer");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_adv) |
+                       reinterpret_cast<uintptr_t>(x_old) | reinterpret_cast<uintptr_t>(grad) |
+                       reinterpret_cast<uintptr_t>(x_new) | reinterpret_cast<uintptr_t>(x_best_adv) |
+                       reinterpret_cast<uintptr_t>(x_best) | reinterpret_cast<uintptr_t>(grad_best);
+  const bool vec = (al % 16 == 0) && (n_per_img % 4 == 0);
+  const int64_t work = vec ? n_per_img / 4 : n_per_img;
+  int gx = (int)((work + 255) / 256);
+  const int cap = (sm_count() * 32 + B - 1) / B;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  dim3 grid(gx, B);
+  if (vec)
+    apgd_step_fused_kernel<true><<<grid, 256, 0, stream>>>(x, x_adv, x_old, grad, step, eps, a, one_minus_a, B,
+                                                           n_per_img, x_new, flags, x_best_adv, x_best, grad_best);
+  else
+    apgd_step_fused_kernel<false><<<grid, 256, 0, stream>>>(x, x_adv, x_old, grad, step, eps, a, one_minus_a, B,
+                                                            n_per_img, x_new, flags, x_best_adv, x_best, grad_best);
   ROBSEG_LAUNCH_CHECK();
   return 0;
 }

@@ -990,6 +990,16 @@ static int launch_generic(const LossParams& p0, cudaStream_t stream, int* tiles_
 
 static int tiles_upper_bound(int B, int64_t HW) { return B * (int)((HW + 31) / 32); }
 
+// shared with loss_up_kernel.cu: fixed-order reduction of per-tile partials into per-image outputs
+int launch_loss_finalize(const float4* partials, int B, int tiles_per_img, const float* grad_scale,
+                         int64_t HW, float* loss_img, float* track_img, int32_t* correct_img,
+                         int32_t* valid_img, cudaStream_t stream) {
+  loss_finalize_kernel<<<B, 256, 0, stream>>>(partials, tiles_per_img, grad_scale, 1.0 / (double)HW,
+                                              loss_img, track_img, correct_img, valid_img);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace robseg
 
 using namespace robseg;

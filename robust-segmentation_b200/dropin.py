@@ -205,8 +205,13 @@ def run_infer_main(argv, overrides=None):
     return ns
 
 
-def fast_logit_upsample(model, head=False):
+def fast_logit_upsample(model, head=False, fuse_loss=False):
     """Route the final logit up-sampling of a reference model through robseg's kernels.
+
+    ``fuse_loss=True`` additionally gives the model a ``forward_lowres(x)`` method returning the
+    logits BEFORE that up-sampling; ``apgd_train`` then runs the loss kernel that interpolates on the
+    fly (``ops.loss_upsampled_fwd_bwd``) and back-propagates from the low-resolution gradient, so
+    the [B,C,H,W] logits and their gradient never exist during an attack.
 
     Works for models shaped like the reference's ``UperNetForSemanticSegmentation``
     (semseg/models/uperforseg.py:382-439: ``backbone`` -> ``decode_head`` -> bilinear
@@ -235,11 +240,22 @@ def fast_logit_upsample(model, head=False):
             low = self.decode_head(feats)
         return ops.upsample_bilinear(low.float(), input.shape[2:])
 
+    def forward_lowres(self, input):
+        if self.training or not input.is_cuda:
+            return None
+        feats = self.backbone(input)
+        if head:
+            with ops.patched_interpolate():
+                return self.decode_head(feats).float()
+        return self.decode_head(feats).float()
+
     model.forward = types.MethodType(forward, model)
+    if fuse_loss:
+        model.forward_lowres = types.MethodType(forward_lowres, model)
     return model
 
 
-def fast_interpolate(model):
+def fast_interpolate(model, fuse_loss=False):
     """Any other reference model (``SegMenter``: semseg/models/segmenter.py:193-231, x16 bilinear
     up-sampling of the class masks at :228; ``PSPNet``): its ``F.interpolate`` calls resolve
     ``torch.nn.functional.interpolate`` at call time, so the whole eval-mode forward runs with that
@@ -255,15 +271,29 @@ def fast_interpolate(model):
         with ops.patched_interpolate():
             return stock_forward(*a, **k)
 
+    def forward_lowres(self, im):
+        # SegMenter.forward up to the class masks (semseg/models/segmenter.py:214-226); the x16
+        # interpolation of :228 is what the fused loss kernel takes over.  Padded inputs (:216) are
+        # cropped after the interpolation by the reference, which the fused kernel does not model.
+        H, W = im.shape[2:]
+        if self.training or not im.is_cuda or H % self.patch_size or W % self.patch_size:
+            return None
+        with ops.patched_interpolate():
+            x = self.encoder(im, pre_neck=True)
+            n_extra = 0 if "SAM" in self.backbone else 1 + self.encoder.distilled
+            return self.decoder(x[:, n_extra:], (H, W)).float()
+
     model.forward = types.MethodType(forward, model)
+    if fuse_loss and all(hasattr(model, n) for n in ("encoder", "decoder", "patch_size", "backbone")):
+        model.forward_lowres = types.MethodType(forward_lowres, model)
     return model
 
 
-def accelerate(model, head=True):
+def accelerate(model, head=True, fuse_loss=False):
     """``fast_logit_upsample`` for UperNet-shaped models, ``fast_interpolate`` otherwise."""
     if hasattr(model, "backbone") and hasattr(model, "decode_head"):
-        return fast_logit_upsample(model, head=head)
-    return fast_interpolate(model)
+        return fast_logit_upsample(model, head=head, fuse_loss=fuse_loss)
+    return fast_interpolate(model, fuse_loss=fuse_loss)
 
 
 def reference_model(kind, variant, n_cls, image_size=512):

@@ -150,6 +150,76 @@ def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=N
     return LossOut(None, None, None, None, dlogits, pred, loss_pix)
 
 
+FUSED_UP_RATIOS = (2, 4, 8, 16)
+
+
+def can_fuse_upsample(low, labels):
+    """True when ``labels`` are an integer x2/4/8/16 up-sampling of fp32 ``low`` [B,C,h,w]."""
+    if low is None or low.dim() != 4 or low.dtype != torch.float32 or not low.is_cuda:
+        return False
+    h, w = low.shape[-2:]
+    H, W = labels.shape[-2:]
+    return H % h == 0 and W % w == 0 and H // h == W // w and H // h in FUSED_UP_RATIOS
+
+
+def loss_upsampled_fwd_bwd(low, labels, kind, weights=None, grad_scale=None, want_grad=True,
+                           want_pred=False, ignore_index=-1, dlow_out=None, want_stats=True):
+    """``loss_fwd_bwd(F.interpolate(low, labels.shape[-2:], mode="bilinear"), ...)`` without the
+    [B,C,H,W] logits: the loss kernel interpolates on the fly and returns the gradient with respect to
+    ``low`` (robseg_loss_upsampled_fwd_bwd).  ``LossOut.dlogits`` is ``dlow``
+    [B,C,h,w]; ratios 2/4/8/16, fp32."""
+    _need_cuda(low, labels, weights)
+    lib = _lib.load()
+    if low.dtype != torch.float32 or low.dim() != 4:
+        raise TypeError("loss_upsampled_fwd_bwd expects 4-D float32 low-resolution logits")
+    low = low.detach().contiguous()
+    B, Cn, h, w = low.shape
+    labels = labels.detach()
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    labels = labels.contiguous()
+    H, W = labels.shape[-2:]
+    if labels.numel() != B * H * W or H % h or W % w or H // h != W // w or H // h not in FUSED_UP_RATIOS:
+        raise ValueError(f"labels {tuple(labels.shape)} are not an integer x2/4/8/16 up-sampling of {tuple(low.shape)}")
+    dev = low.device
+    kid = KIND_IDS[kind]
+    if weights is not None:
+        weights = weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if weights.numel() != Cn:
+            raise ValueError("class weights must have C entries")
+    if grad_scale is not None and not torch.is_tensor(grad_scale):
+        grad_scale = torch.full((B,), float(grad_scale), dtype=torch.float32, device=dev)
+    if grad_scale is not None:
+        grad_scale = grad_scale.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if grad_scale.numel() == 1:
+            grad_scale = grad_scale.reshape(1).expand(B).contiguous()
+    want_grad = want_grad and kid != _lib.LOSS_ARGMAX
+    dlow = None
+    if want_grad:
+        dlow = dlow_out if dlow_out is not None else torch.empty_like(low)
+        if dlow.shape != low.shape or dlow.dtype != low.dtype or not dlow.is_contiguous():
+            raise ValueError("dlow_out must match low")
+    pred = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_pred else None
+    if want_stats:
+        fstat = torch.empty((2, B), dtype=torch.float32, device=dev)
+        istat = torch.empty((2, B), dtype=torch.int32, device=dev)
+    ws = _workspace(dev, lib.robseg_loss_upsampled_workspace_bytes(B, Cn, h, w, H, W))
+    # algorithmic bytes: labels (+ argmax map) + the low-resolution tensors
+    nbytes = 8 * B * H * W * (2 if want_pred else 1) + low.numel() * 4 * (2 if want_grad else 1)
+    with torch.cuda.device(dev), _timed("loss_up_grad" if want_grad else "loss_up_only", nbytes):
+        rc = lib.robseg_loss_upsampled_fwd_bwd(
+            low.data_ptr(), labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn, h, w, H, W,
+            _ptr(grad_scale), _ptr(dlow), _ptr(pred),
+            _ptr(fstat[0]) if want_stats else 0, _ptr(fstat[1]) if want_stats else 0,
+            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0,
+            ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "robseg_loss_upsampled_fwd_bwd")
+    _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0))
+    if want_stats:
+        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlow, pred, None)
+    return LossOut(None, None, None, None, dlow, pred, None)
+
+
 def _f32c(t, name):
     if t.dtype != torch.float32 or not t.is_contiguous():
         raise TypeError(f"{name} must be a contiguous float32 tensor")
@@ -168,6 +238,28 @@ def apgd_step(x, x_adv, x_old, grad, step, eps, a, out):
                                   step.data_ptr(), float(eps), float(a), float(1.0 - a), B,
                                   x[0].numel(), out.data_ptr(), _stream())
     _lib.check(rc, "robseg_apgd_step")
+    _lib.count(1)
+    return out
+
+
+def apgd_step_fused(x, x_adv, x_old, grad, step, eps, a, out, flags, x_best_adv, x_best, grad_best):
+    """``apgd_step`` that first applies the previous iteration's flag-driven row copies
+    (robseg_apgd_step_fused): x_best_adv / x_best / grad_best rows are stored, restarted rows of
+    x_adv / grad are replaced in place.  flags: the [3,B] int32 tensor of ``apgd_bookkeep``."""
+    _need_cuda(x, x_adv, x_old, grad, step, out, flags, x_best_adv, x_best, grad_best)
+    lib = _lib.load()
+    for n, t in (("x", x), ("x_adv", x_adv), ("x_old", x_old), ("grad", grad), ("step", step), ("out", out),
+                 ("x_best_adv", x_best_adv), ("x_best", x_best), ("grad_best", grad_best)):
+        _f32c(t, n)
+    B = x.shape[0]
+    if flags.dtype != torch.int32 or flags.shape != (3, B) or not flags.is_contiguous():
+        raise TypeError("flags must be a contiguous int32 [3,B] tensor")
+    with torch.cuda.device(x.device), _timed("apgd_step", 20 * x.numel()):
+        rc = lib.robseg_apgd_step_fused(x.data_ptr(), x_adv.data_ptr(), x_old.data_ptr(), grad.data_ptr(),
+                                        step.data_ptr(), float(eps), float(a), float(1.0 - a), B, x[0].numel(),
+                                        out.data_ptr(), flags.data_ptr(), x_best_adv.data_ptr(),
+                                        x_best.data_ptr(), grad_best.data_ptr(), _stream())
+    _lib.check(rc, "robseg_apgd_step_fused")
     _lib.count(1)
     return out
 

@@ -11,7 +11,8 @@ execution: per APGD iteration the attack-side work is
                                  d(loss)/d(logits)      (replaces ~7-25 passes, :143-240)
   model backward                 torch.autograd.grad(logits, x, grad_outputs=dlogits)
   K_book  robseg_apgd_bookkeep   device-side flags: no .nonzero()/.sum() host syncs (:485-551)
-  K_rows  robseg_row_select      all boolean-index row copies in one launch
+  (the boolean-index row copies those flags select ride in the NEXT K_step launch --
+   robseg_apgd_step_fused -- and one robseg_row_select flushes them after the last iteration)
 
 The only data-dependent host decision left is ``early_stop`` (:568-569); it is read one
 iteration late from a pinned flag while the device freezes the state itself, so results
@@ -156,15 +157,6 @@ def apgd_schedule(n_iter):
     return checks
 
 
-def _track_values(out, loss_name, track_loss, logits, y, weights):
-    """Per-image value driving best-loss / step-size decisions (attacker.py:353-361,473-475)."""
-    if track_loss in ("ce", "ce-avg"):
-        return out.track_img
-    if track_loss == loss_name:
-        return out.loss_img
-    return ops.loss_fwd_bwd(logits, y, track_loss, weights, want_grad=False).loss_img
-
-
 def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbose=False,
                is_train=False, early_stop=False, track_loss=None, logger=None, y_target=None,
                ignore_index=-1, x_init=None, num_classes=21, weights=None, return_pred=False):
@@ -219,25 +211,44 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     keep_pred = verbose or return_pred
 
     graphed = hasattr(model, "input_grad")  # graphs.GraphedModel: replayed forward / input gradient
+    # dropin.accelerate(model, fuse_loss=True): the model hands out its logits BEFORE the final bilinear
+    # up-sampling and the loss kernel interpolates on the fly (robseg_loss_upsampled_fwd_bwd)
+    lowres = getattr(model, "forward_lowres", None) if not graphed else None
 
     def forward_backward(x_in_buf, need_grad, dbuf):
+        fused = False
         if graphed:
             logits = model(x_in_buf)
         else:
             x_in = x_in_buf.detach().requires_grad_(need_grad)
             with torch.set_grad_enabled(need_grad):
-                logits = model(x_in)
+                logits = lowres(x_in) if lowres is not None else None
+                fused = logits is not None and ops.can_fuse_upsample(logits, y)
+                if not fused:
+                    logits = model(x_in)
         if logits.dtype not in (torch.float32, torch.bfloat16):
             logits = logits.float()  # fp16 under autocast: F.cross_entropy up-casts too (attacker.py:147)
-        out = ops.loss_fwd_bwd(logits, y, loss, w_dev, want_grad=need_grad, want_pred=keep_pred,
-                               dlogits_out=dbuf)
+        if fused:
+            def run(kind, **kw):
+                return ops.loss_upsampled_fwd_bwd(logits, y, kind, w_dev, **kw)
+            out = run(loss, want_grad=need_grad, want_pred=keep_pred, dlow_out=dbuf)
+        else:
+            def run(kind, **kw):
+                return ops.loss_fwd_bwd(logits, y, kind, w_dev, **kw)
+            out = run(loss, want_grad=need_grad, want_pred=keep_pred, dlogits_out=dbuf)
         g = None
         if need_grad:
             if graphed:
                 g = model.input_grad(out.dlogits).clone()
             else:
                 (g,) = torch.autograd.grad(logits, [x_in], grad_outputs=out.dlogits)
-        track = _track_values(out, loss, track_loss, logits, y, w_dev)
+        # per-image value driving best-loss / step-size decisions (attacker.py:353-361,473-475)
+        if track_loss in ("ce", "ce-avg"):
+            track = out.track_img
+        elif track_loss == loss:
+            track = out.loss_img
+        else:
+            track = run(track_loss, want_grad=False).loss_img
         return out, g, track, logits
 
     # ---- initial point (attacker.py:342-383) ------------------------------------------------
@@ -268,10 +279,16 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     copied = None
     checks = apgd_schedule(n_iter)
 
+    pending = False  # row copies of the previous iteration, folded into the next step launch
     for i in range(n_iter):
         # ---- gradient step (attacker.py:388-410) ---------------------------------------------
         a = 0.75 if i > 0 else 1.0
-        ops.apgd_step(x, x_adv, x_old, grad, step, eps, a, x_new)
+        if pending:
+            # + the previous iteration's x_best_adv / x_best / grad_best row stores and restart rows
+            # (:494-495,523-525,546-548): the step reads x_adv and grad anyway
+            ops.apgd_step_fused(x, x_adv, x_old, grad, step, eps, a, x_new, flags, x_best_adv, x_best, grad_best)
+        else:
+            ops.apgd_step(x, x_adv, x_old, grad, step, eps, a, x_new)
         x_old, x_adv, x_new = x_adv, x_new, x_old
 
         # ---- forward, fused loss, backward (attacker.py:459-475) -----------------------------
@@ -284,18 +301,9 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
         ops.apgd_bookkeep(out.correct, out.valid, track, acc, loss_best, loss_best_last,
                           reduced_last, step, loss_steps, i, checks.get(i, 0), n_pxl, early_stop,
                           flags, done)
-        jobs = [(x_best_adv, x_adv, flags[0], None),
-                (x_best, x_adv, flags[1], None),
-                (grad_best, grad, flags[1], None)]
+        pending = True
         if keep_pred:
-            jobs.append((pred_best, out.pred, flags[0], None))
-        ops.row_select(jobs, bs, device)
-        if i in checks:
-            # restart the halved rows from their best point (:546-548).  A separate launch: these
-            # jobs WRITE x_adv, which the x_best_adv job above reads for the same row when the
-            # accuracy improved but the loss did not -- stream order keeps the reference's sequence.
-            ops.row_select([(x_adv, x_best, flags[2], flags[1]), (grad, grad_best, flags[2], flags[1])],
-                           bs, device)
+            ops.row_select([(pred_best, out.pred, flags[0], None)], bs, device)
 
         if verbose:
             m_acc, a_acc, m_iou = compute_iou_acc(pred_best, y, n_cls, ignore_index=ignore_index)
@@ -315,6 +323,9 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
             copied = torch.cuda.Event()
             copied.record()
 
+    if pending:  # the last iteration's row stores (restart copies only matter to a following step)
+        ops.row_select([(x_best_adv, x_adv, flags[0], None), (x_best, x_adv, flags[1], None),
+                        (grad_best, grad, flags[1], None)], bs, device)
     if return_pred:
         return x_best, acc, loss_best, x_best_adv, pred_best
     return x_best, acc, loss_best, x_best_adv

@@ -5,3 +5,5 @@ mkdir -p gpurun_out
 (timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err); tail -c 3000 gpurun_out/r2a_bench.json; tail -3 gpurun_out/r2a_bench.err
 (timeout 600 python bench.py --workload pirat --steps 3 --warmup 3 > gpurun_out/r2a_pirat.json 2> gpurun_out/r2a_pirat.err); tail -c 2500 gpurun_out/r2a_pirat.json; tail -3 gpurun_out/r2a_pirat.err
 (timeout 600 python bench.py --model segmenter --steps 1 --warmup 3 > gpurun_out/r2a_segmenter.json 2> gpurun_out/r2a_segmenter.err); tail -c 2500 gpurun_out/r2a_segmenter.json; tail -3 gpurun_out/r2a_segmenter.err
+(timeout 600 python -m pytest tests/test_gpu_fused_upsample.py -m gpu -q --timeout 300 2>&1 | tail -30 > gpurun_out/r2a_pytest_fused.log); tail -15 gpurun_out/r2a_pytest_fused.log
+for a in "16 150 128 4" "16 150 32 16" "16 150 64 8" "2 21 128 4" "16 150 128 4 js-avg"; do timeout 200 python scripts/loss_up_probe.py $a 2>&1 | tail -1 | tee -a gpurun_out/r2a_loss_up_probe.log; done
