@@ -140,6 +140,34 @@ int robseg_apgd_step_fused(const float* x, float* x_adv, const float* x_old, flo
                            float* x_best, float* grad_best, robseg_stream_t stream);
 
 /*
+ * CUDA-graph forms of the two launches whose arguments change from one APGD iteration to the next
+ * (one captured graph per iteration, semseg/attacker.py:385-551).  The
+ * per-iteration scalars live in a DEVICE control block of int32 words that the bookkeeping kernel itself
+ * advances, so the captured launches are identical for every iteration and every stage:
+ *   ctl[ROBSEG_CTL_ITER]       iteration index i (a = 1.0 at i = 0, else 0.75: attacker.py:387)
+ *   ctl[ROBSEG_CTL_NITER]      n_iter of the stage (rows of loss_steps in use)
+ *   ctl[ROBSEG_CTL_EPS]        eps of the stage, float bits
+ *   ctl[ROBSEG_CTL_SCHED + i]  window k if the step-size check fires at iteration i, else 0
+ * robseg_apgd_step_ctl = robseg_apgd_step_fused with a / eps from ctl and NO buffer rotation: x_old <- x_adv
+ * and x_adv <- new point are written in place (a captured graph needs fixed addresses).
+ * robseg_apgd_bookkeep_ctl = robseg_apgd_bookkeep with (iter, check_k, n_iter) from ctl; it increments
+ * ctl[ROBSEG_CTL_ITER] when it is done.  The host writes ctl once per stage.
+ */
+#define ROBSEG_CTL_ITER 0
+#define ROBSEG_CTL_NITER 1
+#define ROBSEG_CTL_EPS 2
+#define ROBSEG_CTL_SCHED 8
+#define ROBSEG_CTL_MAX_ITER 4096
+int robseg_apgd_step_ctl(const float* x, float* x_adv, float* x_old, float* grad, const float* step,
+                         const int32_t* ctl, int B, int64_t n_per_img, const int32_t* flags,
+                         float* x_best_adv, float* x_best, float* grad_best, robseg_stream_t stream);
+int robseg_apgd_bookkeep_ctl(const int32_t* correct, const int32_t* valid, const float* loss_indiv,
+                             float* acc, float* loss_best, float* loss_best_last, float* reduced_last,
+                             float* step, float* loss_steps, int32_t* ctl, int B, int64_t HW,
+                             int early_stop, int32_t* flags_out, int32_t* done_flag,
+                             robseg_stream_t stream);
+
+/*
  * z <- clip01(x + clip(z - x, -eps, eps)): the stage hand-off of apgd_largereps
  * (semseg/attacker.py:683-690).  With noise != NULL computes the random start instead,
  * out = clip01(x + eps*noise) (semseg/attacker.py:292-294, noise = 2*rand-1).

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librobseg_b200.so")
 ABI_VERSION = 1
 MAX_ROW_JOBS = 8
+CTL_ITER, CTL_NITER, CTL_EPS, CTL_SCHED, CTL_MAX_ITER = 0, 1, 2, 8, 4096
 
 F32, BF16 = 0, 1
 LOSS_CE, LOSS_MASK_CE, LOSS_MASK_CE_BAL, LOSS_JS, LOSS_ARGMAX = 0, 1, 2, 3, 4
@@ -34,6 +35,8 @@ SIGNATURES = {
                                            _p, _p, _sz, _p]),
     "robseg_apgd_step": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p]),
     "robseg_apgd_step_fused": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p, _p, _p, _p, _p]),
+    "robseg_apgd_step_ctl": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _p, _p, _p]),
+    "robseg_apgd_bookkeep_ctl": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p]),
     "robseg_project_linf": (_i, [_p, _p, _p, _f, _i64, _p, _p]),
     "robseg_pgd_step": (_i, [_p, _p, _p, _f, _f, _i, _i, _i64, _p, _p]),
     "robseg_apgd_bookkeep": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i64, _i,

@@ -117,6 +117,67 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// CUDA-graph form of the iteration's first launch: every per-iteration scalar comes
+// from the device control block ctl (robseg_b200.h: [0] iteration, [2] eps bits), the buffers never rotate
+// -- x_old <- x_adv and x_adv <- new point are written in place by the thread that read them -- so the same
+// captured launch is valid for every iteration of every stage.  Includes the folded row copies above.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+    apgd_step_ctl_kernel(const float* __restrict__ x, float* xa_io, float* xo_io, float* g_io,
+                         const float* __restrict__ step, const int32_t* __restrict__ ctl, int B,
+                         int64_t n_per_img, const int32_t* __restrict__ flags, float* x_best_adv,
+                         float* x_best, float* grad_best) {
+  const int b = blockIdx.y;
+  const float st = __ldg(step + b);
+  const float a = __ldg(ctl + ROBSEG_CTL_ITER) == 0 ? 1.0f : 0.75f, oma = 1.0f - a;
+  const float eps = __int_as_float(__ldg(ctl + ROBSEG_CTL_EPS));
+  const bool f_adv = __ldg(flags + b) != 0, f_best = __ldg(flags + B + b) != 0;
+  const bool f_restart = __ldg(flags + 2 * B + b) != 0 && !f_best;
+  const int64_t base = (int64_t)b * n_per_img;
+  if constexpr (VEC4) {
+    const int64_t n4 = n_per_img >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    float4* a4 = reinterpret_cast<float4*>(xa_io + base);
+    float4* o4 = reinterpret_cast<float4*>(xo_io + base);
+    float4* g4 = reinterpret_cast<float4*>(g_io + base);
+    float4* ba4 = reinterpret_cast<float4*>(x_best_adv + base);
+    float4* bx4 = reinterpret_cast<float4*>(x_best + base);
+    float4* bg4 = reinterpret_cast<float4*>(grad_best + base);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 vx = __ldcs(x4 + i), vo = o4[i];
+      float4 va = a4[i], vg = g4[i];
+      if (f_adv) ba4[i] = va;
+      if (f_best) bx4[i] = va, bg4[i] = vg;
+      if (f_restart) {
+        va = bx4[i], vg = bg4[i];
+        g4[i] = vg;
+      }
+      float4 r;
+      r.x = apgd_elem(vx.x, va.x, vo.x, vg.x, st, eps, a, oma);
+      r.y = apgd_elem(vx.y, va.y, vo.y, vg.y, st, eps, a, oma);
+      r.z = apgd_elem(vx.z, va.z, vo.z, vg.z, st, eps, a, oma);
+      r.w = apgd_elem(vx.w, va.w, vo.w, vg.w, st, eps, a, oma);
+      o4[i] = va;
+      a4[i] = r;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      float va = xa_io[base + i], vg = g_io[base + i];
+      const float vo = xo_io[base + i];
+      if (f_adv) x_best_adv[base + i] = va;
+      if (f_best) x_best[base + i] = va, grad_best[base + i] = vg;
+      if (f_restart) {
+        va = x_best[base + i], vg = grad_best[base + i];
+        g_io[base + i] = vg;
+      }
+      xo_io[base + i] = va;
+      xa_io[base + i] = apgd_elem(x[base + i], va, vo, vg, st, eps, a, oma);
+    }
+  }
+}
+
 // out = clip01(x + clip(z-x, +-eps))   or, with noise, clip01(x + eps*noise)
 __global__ void __launch_bounds__(256)
     project_kernel(const float* __restrict__ z, const float* __restrict__ x,
@@ -164,8 +225,14 @@ __global__ void __launch_bounds__(1024)
                          const float* __restrict__ loss_indiv, float* acc, float* loss_best,
                          float* loss_best_last, float* reduced_last, float* step,
                          float* loss_steps, int n_iter, int iter, int check_k, int B, int64_t HW,
-                         int early_stop, int32_t* flags, int32_t* done_flag, int32_t* done_host) {
+                         int early_stop, int32_t* flags, int32_t* done_flag, int32_t* done_host,
+                         int32_t* ctl) {
   __shared__ int sh_any_nonzero;
+  if (ctl != nullptr) {  // CUDA-graph form: iteration, its check window and the stage length live on the device
+    iter = ctl[ROBSEG_CTL_ITER];
+    n_iter = ctl[ROBSEG_CTL_NITER];
+    check_k = ctl[ROBSEG_CTL_SCHED + iter];
+  }
   const bool done = *done_flag != 0;
   if (threadIdx.x == 0) sh_any_nonzero = 0;
   __syncthreads();
@@ -216,6 +283,8 @@ __global__ void __launch_bounds__(1024)
       __threadfence_system();
     }
   }
+  // every thread read ctl before the barrier above; the next replay sees the next iteration
+  if (threadIdx.x == 0 && ctl != nullptr && iter + 1 < ROBSEG_CTL_MAX_ITER) ctl[ROBSEG_CTL_ITER] = iter + 1;
 }
 
 struct RowJobs {
@@ -362,7 +431,56 @@ extern "C" int robseg_apgd_bookkeep(const int32_t* correct, const int32_t* valid
   apgd_bookkeep_kernel<<<1, threads, 0, stream>>>(correct, valid, loss_indiv, acc, loss_best,
                                                   loss_best_last, reduced_last, step, loss_steps,
                                                   n_iter, iter, check_k, B, HW, early_stop,
-                                                  flags_out, done_flag, done_host);
+                                                  flags_out, done_flag, done_host, nullptr);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int robseg_apgd_bookkeep_ctl(const int32_t* correct, const int32_t* valid,
+                                        const float* loss_indiv, float* acc, float* loss_best,
+                                        float* loss_best_last, float* reduced_last, float* step,
+                                        float* loss_steps, int32_t* ctl, int B, int64_t HW,
+                                        int early_stop, int32_t* flags_out, int32_t* done_flag,
+                                        robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(correct && valid && loss_indiv && acc && loss_best && loss_best_last && reduced_last &&
+                     step && loss_steps && flags_out && done_flag && ctl,
+                 "NULL pointer");
+  ROBSEG_REQUIRE(B > 0 && HW > 0, "bad arguments B=%d", B);
+  int threads = ((B + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  apgd_bookkeep_kernel<<<1, threads, 0, stream>>>(correct, valid, loss_indiv, acc, loss_best,
+                                                  loss_best_last, reduced_last, step, loss_steps, 0, 0, 0,
+                                                  B, HW, early_stop, flags_out, done_flag, nullptr, ctl);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int robseg_apgd_step_ctl(const float* x, float* x_adv, float* x_old, float* grad,
+                                    const float* step, const int32_t* ctl, int B, int64_t n_per_img,
+                                    const int32_t* flags, float* x_best_adv, float* x_best,
+                                    float* grad_best, robseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ROBSEG_REQUIRE(x && x_adv && x_old && grad && step && ctl && flags && x_best_adv && x_best && grad_best,
+                 "NULL pointer");
+  ROBSEG_REQUIRE(B > 0 && B <= 65535 && n_per_img > 0, "bad shape B=%d n=%lld", B, (long long)n_per_img);
+  ROBSEG_REQUIRE(x_adv != x && x_old != x && x_old != x_adv, "x / x_adv / x_old must be distinct buffers");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_adv) |
+                       reinterpret_cast<uintptr_t>(x_old) | reinterpret_cast<uintptr_t>(grad) |
+                       reinterpret_cast<uintptr_t>(x_best_adv) | reinterpret_cast<uintptr_t>(x_best) |
+                       reinterpret_cast<uintptr_t>(grad_best);
+  const bool vec = (al % 16 == 0) && (n_per_img % 4 == 0);
+  const int64_t work = vec ? n_per_img / 4 : n_per_img;
+  int gx = (int)((work + 255) / 256);
+  const int cap = (sm_count() * 32 + B - 1) / B;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  dim3 grid(gx, B);
+  if (vec)
+    apgd_step_ctl_kernel<true><<<grid, 256, 0, stream>>>(x, x_adv, x_old, grad, step, ctl, B, n_per_img, flags,
+                                                         x_best_adv, x_best, grad_best);
+  else
+    apgd_step_ctl_kernel<false><<<grid, 256, 0, stream>>>(x, x_adv, x_old, grad, step, ctl, B, n_per_img, flags,
+                                                          x_best_adv, x_best, grad_best);
   ROBSEG_LAUNCH_CHECK();
   return 0;
 }

@@ -1,4 +1,15 @@
-"""CUDA-graph replay of the consumer around the hot path.
+"""CUDA-graph replay of one APGD iteration.
+
+:class:`GraphedAttack` -- reached through ``GraphedModel.attack`` and used by ``apgd_train`` whenever the
+model is a :class:`GraphedModel` -- captures the WHOLE iteration of semseg/attacker.py:385-551 as one graph:
+image update (+ the previous iteration's row copies) -> model forward -> fused loss -> input-gradient
+backward -> device bookkeeping.  What changes between iterations (iteration index, momentum a, the
+check window k, the stage's eps and length) lives in a device control block that the bookkeeping kernel
+advances itself (``robseg_apgd_step_ctl`` / ``robseg_apgd_bookkeep_ctl``), and the image buffers are
+rotated in place, so the same two graphs (with / without backward) serve every iteration of every stage.
+Per iteration the host issues one graph launch and the early-stop poll.
+
+:class:`GraphedModel` alone (the first version of this row) replays only the consumer:
 
 One APGD iteration is: image update -> ``model(x_adv)`` -> fused loss -> ``d logits / d x_adv``
 -> bookkeeping (semseg/attacker.py:385-551).  The robseg kernels are a handful of launches; the
@@ -71,3 +82,157 @@ class GraphedModel:
             self.gout.copy_(gout)
         self.bwd.replay()
         return self.gx
+
+
+    def attack(self, keep_pred, early_stop, n_iter):
+        """The :class:`GraphedAttack` for this model / batch shape (cached)."""
+        key = (bool(keep_pred), bool(early_stop))
+        cache = self.__dict__.setdefault("_attacks", {})
+        ga = cache.get(key)
+        if ga is None or ga.n_iter_max < n_iter:
+            ga = cache[key] = GraphedAttack(self, keep_pred, early_stop, max(512, n_iter))
+        return ga
+
+
+class GraphedAttack:
+    """Static state + three captured graphs per loss kind (initial point, iteration with backward,
+    last iteration without) sharing one memory pool.  See the module docstring."""
+
+    def __init__(self, gm, keep_pred, early_stop, n_iter_max):
+        from . import ops
+
+        self.gm, self.model = gm, gm.model
+        self.keep_pred, self.early_stop, self.n_iter_max = bool(keep_pred), bool(early_stop), int(n_iter_max)
+        x = gm.x
+        dev = x.device
+        B = x.shape[0]
+        self.B, self.n_pxl = B, x.shape[-2] * x.shape[-1]
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+        self.x = torch.zeros_like(x, requires_grad=False)
+        self.x_adv = torch.zeros_like(x).requires_grad_(True)  # the captured model input (leaf)
+        self.x_old, self.x_best, self.x_best_adv = (torch.zeros_like(self.x) for _ in range(3))
+        self.grad, self.grad_best = torch.zeros_like(self.x), torch.zeros_like(self.x)
+        self.y = torch.zeros((B,) + tuple(x.shape[2:]), dtype=torch.int64, device=dev)
+        self.acc, self.loss_best, self.loss_best_last, self.reduced_last, self.step = (z(B) for _ in range(5))
+        self.loss_steps = z(self.n_iter_max, B)
+        self.flags, self.done = z(3, B, dt=torch.int32), z(1, dt=torch.int32)
+        self.ctl = ops.make_ctl(self.n_iter_max, dev)
+        self.done_host = torch.zeros([1], dtype=torch.int32).pin_memory()
+        self.pred_best = torch.zeros_like(self.y) if keep_pred else None
+        self.weights = None  # [C] class weights, allocated on first use
+        self.pool = None
+        self.graphs = {}     # loss kind -> dict(init=, it=, last=, out0=)
+
+    # ---- one iteration, as launched eagerly for warm-up and under capture -------------------------
+    def _body(self, kind, track_loss, with_step, with_grad):
+        from . import ops
+
+        if with_step:
+            ops.apgd_step_ctl(self.x, self.x_adv.detach(), self.x_old, self.grad, self.step, self.ctl, self.flags,
+                              self.x_best_adv, self.x_best, self.grad_best)
+        lowres = getattr(self.model, "forward_lowres", None)
+        with torch.set_grad_enabled(with_grad):
+            logits = lowres(self.x_adv) if lowres is not None else None
+            fused = logits is not None and ops.can_fuse_upsample(logits, self.y)
+            if not fused:
+                logits = self.model(self.x_adv)
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        w = self.weights if kind == "mask-ce-bal" else None
+        fn = ops.loss_upsampled_fwd_bwd if fused else ops.loss_fwd_bwd
+        out = fn(logits, self.y, kind, w, want_grad=with_grad, want_pred=self.keep_pred)
+        if with_grad:
+            (gx,) = torch.autograd.grad(logits, [self.x_adv], grad_outputs=out.dlogits)
+            self.grad.copy_(gx)
+        track = out.track_img if track_loss in ("ce", "ce-avg") else out.loss_img
+        if with_step:
+            ops.apgd_bookkeep_ctl(out.correct, out.valid, track, self.acc, self.loss_best, self.loss_best_last,
+                                  self.reduced_last, self.step, self.loss_steps, self.ctl, self.n_pxl,
+                                  self.early_stop, self.flags, self.done)
+            if self.keep_pred:
+                ops.row_select([(self.pred_best, out.pred, self.flags[0], None)], self.B, self.x.device)
+        return out, track
+
+    def _capture(self, kind, track_loss):
+        params = list(self.model.parameters())
+        req = [p.requires_grad for p in params]
+        for p in params:  # the attack differentiates w.r.t. the input only (attacker.py:350,469)
+            p.requires_grad_(False)
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up off the capture stream (cuDNN plans, workspaces)
+                for _ in range(2):
+                    self._body(kind, track_loss, True, True)
+                    self._body(kind, track_loss, True, False)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = {}
+            for name, (with_step, with_grad) in (("init", (False, True)), ("it", (True, True)), ("last", (True, False))):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, pool=self.pool):
+                    out, track = self._body(kind, track_loss, with_step, with_grad)
+                if self.pool is None:
+                    self.pool = graph.pool()
+                g[name] = graph
+                if name == "init":
+                    g["out0"], g["track0"] = out, track
+            self.graphs[(kind, track_loss)] = g
+        finally:
+            for p, r in zip(params, req):
+                p.requires_grad_(r)
+        return g
+
+    def run_stage(self, x, y, x_adv0, eps, n_iter, kind, track_loss, weights, checks):
+        """One ``apgd_train`` call (a stage of apgd_largereps) from the starting point ``x_adv0``.
+        Returns fresh tensors ``(x_best, acc, loss_best, x_best_adv, pred_best)``."""
+        from . import ops
+
+        if n_iter > self.n_iter_max:
+            raise ValueError("stage longer than the captured control block")
+        with torch.no_grad():
+            self.x.copy_(x)
+            self.y.copy_(y)
+            if weights is not None and kind == "mask-ce-bal":
+                if self.weights is None:
+                    self.weights = torch.empty_like(weights)
+                    self.graphs = {k: v for k, v in self.graphs.items() if k[0] != "mask-ce-bal"}
+                self.weights.copy_(weights)
+            # (capturing warms the iteration up eagerly, which moves x_adv: set the start point afterwards)
+            g = self.graphs.get((kind, track_loss)) or self._capture(kind, track_loss)
+            self.x_adv.copy_(x_adv0)
+            ops.set_ctl(self.ctl, n_iter, eps, checks)
+            self.loss_steps.zero_()
+            self.flags.zero_()
+            self.done.zero_()
+            g["init"].replay()
+            out0, track0 = g["out0"], g["track0"]
+            # initial state (attacker.py:362-383); -1 pixels count as wrong here (:370-371)
+            self.acc.copy_(out0.correct.float() / torch.full((), float(self.n_pxl), device=self.x.device))
+            self.loss_best.copy_(track0)
+            self.loss_best_last.copy_(track0)
+            self.reduced_last.fill_(1.0)
+            self.step.fill_(2.0 * eps)
+            for t in (self.x_best, self.x_best_adv, self.x_old):
+                t.copy_(self.x_adv)
+            self.grad_best.copy_(self.grad)
+            if self.keep_pred:
+                self.pred_best.copy_(out0.pred)
+            copied = None
+            for i in range(n_iter):
+                g["it" if i < n_iter - 1 else "last"].replay()
+                if self.early_stop:  # polled one iteration late; the device freezes the state itself
+                    if copied is not None:
+                        copied.synchronize()
+                        if int(self.done_host[0]) != 0:
+                            break
+                    self.done_host.copy_(self.done, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record()
+            if n_iter > 0:  # the last iteration's pending row stores
+                xa = self.x_adv.detach()
+                ops.row_select([(self.x_best_adv, xa, self.flags[0], None), (self.x_best, xa, self.flags[1], None),
+                                (self.grad_best, self.grad, self.flags[1], None)], self.B, self.x.device)
+            return (self.x_best.clone(), self.acc.clone(), self.loss_best.clone(), self.x_best_adv.clone(),
+                    self.pred_best.clone() if self.keep_pred else None)

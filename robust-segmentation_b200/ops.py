@@ -264,6 +264,57 @@ def apgd_step_fused(x, x_adv, x_old, grad, step, eps, a, out, flags, x_best_adv,
     return out
 
 
+def make_ctl(n_iter_max, device):
+    """Device control block of the CUDA-graph iteration (robseg_b200.h ROBSEG_CTL_*)."""
+    if n_iter_max > _lib.CTL_MAX_ITER:
+        raise ValueError(f"n_iter {n_iter_max} exceeds ROBSEG_CTL_MAX_ITER")
+    return torch.zeros(_lib.CTL_SCHED + n_iter_max, dtype=torch.int32, device=device)
+
+
+def set_ctl(ctl, n_iter, eps, checks):
+    """Start a stage: iteration 0, its length, eps and the check schedule {iteration: window k}
+    (one small pinned-host -> device copy, stream ordered)."""
+    import struct
+
+    host = torch.zeros(ctl.numel(), dtype=torch.int32)
+    host[_lib.CTL_NITER] = n_iter
+    host[_lib.CTL_EPS] = struct.unpack("i", struct.pack("f", float(eps)))[0]
+    for it, k in checks.items():
+        host[_lib.CTL_SCHED + it] = k
+    ctl.copy_(host.pin_memory(), non_blocking=True)
+    return ctl
+
+
+def apgd_step_ctl(x, x_adv, x_old, grad, step, ctl, flags, x_best_adv, x_best, grad_best):
+    """In-place, device-controlled form of ``apgd_step_fused`` (robseg_apgd_step_ctl): x_old <- x_adv,
+    x_adv <- new point; a / eps come from ``ctl``.  Fixed addresses, so it can sit in a CUDA graph."""
+    lib = _lib.load()
+    for n, t in (("x", x), ("x_adv", x_adv), ("x_old", x_old), ("grad", grad), ("step", step),
+                 ("x_best_adv", x_best_adv), ("x_best", x_best), ("grad_best", grad_best)):
+        _f32c(t, n)
+    B = x.shape[0]
+    with torch.cuda.device(x.device), _timed("apgd_step", 24 * x.numel()):
+        rc = lib.robseg_apgd_step_ctl(x.data_ptr(), x_adv.data_ptr(), x_old.data_ptr(), grad.data_ptr(),
+                                      step.data_ptr(), ctl.data_ptr(), B, x[0].numel(), flags.data_ptr(),
+                                      x_best_adv.data_ptr(), x_best.data_ptr(), grad_best.data_ptr(), _stream())
+    _lib.check(rc, "robseg_apgd_step_ctl")
+    _lib.count(1)
+
+
+def apgd_bookkeep_ctl(correct, valid, loss_indiv, acc, loss_best, loss_best_last, reduced_last, step,
+                      loss_steps, ctl, HW, early_stop, flags, done):
+    """``apgd_bookkeep`` with (iter, check_k, n_iter) read from -- and iter advanced in -- ``ctl``."""
+    lib = _lib.load()
+    B = acc.shape[0]
+    with torch.cuda.device(acc.device), _timed("bookkeep", 0):
+        rc = lib.robseg_apgd_bookkeep_ctl(
+            correct.data_ptr(), valid.data_ptr(), loss_indiv.data_ptr(), acc.data_ptr(), loss_best.data_ptr(),
+            loss_best_last.data_ptr(), reduced_last.data_ptr(), step.data_ptr(), loss_steps.data_ptr(),
+            ctl.data_ptr(), B, int(HW), int(bool(early_stop)), flags.data_ptr(), done.data_ptr(), _stream())
+    _lib.check(rc, "robseg_apgd_bookkeep_ctl")
+    _lib.count(1)
+
+
 def project_linf(z, x, eps, noise=None, out=None):
     """clip01(x + clip(z-x, +-eps)), or with noise: clip01(x + eps*noise) (robseg_project_linf)."""
     _need_cuda(z, x, noise, out)

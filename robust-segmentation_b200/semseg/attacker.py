@@ -211,6 +211,11 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     keep_pred = verbose or return_pred
 
     graphed = hasattr(model, "input_grad")  # graphs.GraphedModel: replayed forward / input gradient
+    if graphed and hasattr(model, "attack") and not verbose and track_loss in ("ce", "ce-avg", loss):
+        # the whole iteration as one CUDA graph (graphs.GraphedAttack)
+        res = model.attack(keep_pred, early_stop, n_iter).run_stage(
+            x, y, x_adv, eps, n_iter, loss, track_loss, w_dev, apgd_schedule(n_iter))
+        return res if return_pred else res[:4]
     # dropin.accelerate(model, fuse_loss=True): the model hands out its logits BEFORE the final bilinear
     # up-sampling and the loss kernel interpolates on the fly (robseg_loss_upsampled_fwd_bwd)
     lowres = getattr(model, "forward_lowres", None) if not graphed else None
