@@ -65,6 +65,7 @@ __device__ __forceinline__ constexpr float row_w(int r) {
 template <int R>
 __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
   constexpr int NDC = 32 / R;  // dual cells per warp tile
+  constexpr int CU = R >= 16 ? 1 : (R == 8 ? 2 : 4);  // channels per loop trip (independent chains)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
   const int C = p.C;
@@ -92,10 +93,11 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
     {
       const float* base = p.low + (size_t)b * C * p.h * p.w;
       const int n_items = C * NDC;
-      for (int i0 = 0; i0 < n_items; i0 += 32 * 4) {
-        float va[4], vb[4], vc[4], vd[4];
+      constexpr int FU = 8;  // items (32 scalar loads) in flight per lane
+      for (int i0 = 0; i0 < n_items; i0 += 32 * FU) {
+        float va[FU], vb[FU], vc[FU], vd[FU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < FU; ++u) {
           const int i = i0 + u * 32 + lane;
           if (i < n_items) {
             const int c = i / NDC, d = i - c * NDC;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < FU; ++u) {
           const int i = i0 + u * 32 + lane;
           if (i < n_items) tab[i] = make_float4(va[u], vb[u] - va[u], vc[u], vd[u] - vc[u]);
         }
@@ -142,22 +144,37 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
         }
       }
     } else {
+      // few rows per lane (small R) leave few independent chains: unroll CU channel pairs per trip with
+      // separate accumulators (ncu, x4: 44 % issue utilisation with one pair per trip, stalled on the
+      // 4-cycle dependent-issue wait and the LDS / MUFU scoreboards)
+      float m2[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) m2[r] = -INFINITY;
       int c = 0;
 #pragma unroll 1
-      for (; c + 2 <= C; c += 2) {
-        const float4 q0 = col[c * NDC], q1 = col[(c + 1) * NDC];
-        const float top0 = fmaf(lx, q0.y, q0.x), dif0 = fmaf(lx, q0.w, q0.z) - top0;
-        const float top1 = fmaf(lx, q1.y, q1.x), dif1 = fmaf(lx, q1.w, q1.z) - top1;
+      for (; c + 2 * CU <= C; c += 2 * CU) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          m[r] = fmax3u(m[r], fmaf(row_w<R>(r), dif0, top0), fmaf(row_w<R>(r), dif1, top1));
+        for (int u = 0; u < CU; ++u) {
+          const float4 q0 = col[(c + 2 * u) * NDC], q1 = col[(c + 2 * u + 1) * NDC];
+          const float top0 = fmaf(lx, q0.y, q0.x), dif0 = fmaf(lx, q0.w, q0.z) - top0;
+          const float top1 = fmaf(lx, q1.y, q1.x), dif1 = fmaf(lx, q1.w, q1.z) - top1;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float z0 = fmaf(row_w<R>(r), dif0, top0), z1 = fmaf(row_w<R>(r), dif1, top1);
+            if (u & 1) m2[r] = fmax3u(m2[r], z0, z1);
+            else m[r] = fmax3u(m[r], z0, z1);
+          }
+        }
       }
-      if (c < C) {
+#pragma unroll 1
+      for (; c < C; ++c) {
         const float4 q = col[c * NDC];
         const float top = fmaf(lx, q.y, q.x), dif = fmaf(lx, q.w, q.z) - top;
 #pragma unroll
         for (int r = 0; r < R; ++r) m[r] = fmaxf(m[r], fmaf(row_w<R>(r), dif, top));
       }
+#pragma unroll
+      for (int r = 0; r < R; ++r) m[r] = fmaxf(m[r], m2[r]);
     }
 
     float loss_sum = 0.f, ce_sum = 0.f;
@@ -170,18 +187,50 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
       }
     } else {
       // ---- pass 2: sum of exp(z - max) + first maximal channel (equality, walking downwards) -------
+      constexpr int kNoIdx = 0x7fffffff;
       float mL[R], s[R];
+      {
+        float su[CU][R];
+        int au[CU][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) mL[r] = m[r] * kLog2eU, s[r] = 0.f;
+        for (int r = 0; r < R; ++r) mL[r] = m[r] * kLog2eU;
+#pragma unroll
+        for (int u = 0; u < CU; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r) su[u][r] = 0.f, au[u][r] = kNoIdx;
+        int c = C;
 #pragma unroll 1
-      for (int c = C - 1; c >= 0; --c) {
-        const float4 q = col[c * NDC];
-        const float top = fmaf(lx, q.y, q.x), dif = fmaf(lx, q.w, q.z) - top;
+        for (; c - CU >= 0; c -= CU) {
+#pragma unroll
+          for (int u = 0; u < CU; ++u) {
+            const int cu = c - 1 - u;
+            const float4 q = col[cu * NDC];
+            const float top = fmaf(lx, q.y, q.x), dif = fmaf(lx, q.w, q.z) - top;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float z = fmaf(row_w<R>(r), dif, top);
+              su[u][r] += ex2_approx(fmaf(z, kLog2eU, -mL[r]));
+              au[u][r] = (z == m[r]) ? cu : au[u][r];  // walking downwards: the last hit is the lowest
+            }
+          }
+        }
+#pragma unroll 1
+        for (; c > 0; --c) {
+          const float4 q = col[(c - 1) * NDC];
+          const float top = fmaf(lx, q.y, q.x), dif = fmaf(lx, q.w, q.z) - top;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float z = fmaf(row_w<R>(r), dif, top);
+            su[0][r] += ex2_approx(fmaf(z, kLog2eU, -mL[r]));
+            au[0][r] = (z == m[r]) ? (c - 1) : au[0][r];
+          }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float z = fmaf(row_w<R>(r), dif, top);
-          s[r] += ex2_approx(fmaf(z, kLog2eU, -mL[r]));
-          amx[r] = (z == m[r]) ? c : amx[r];
+          s[r] = su[0][r], amx[r] = au[0][r];
+#pragma unroll
+          for (int u = 1; u < CU; ++u) s[r] += su[u][r], amx[r] = min(amx[r], au[u][r]);
+          amx[r] = amx[r] == kNoIdx ? 0 : amx[r];  // (only NaN logits have no channel equal to the maximum)
         }
       }
       // ---- per-pixel loss terms (same formulas as loss_kernel.cu) ---------------
@@ -228,7 +277,7 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
         float4* out = p.contrib + (((size_t)b * (p.h + 1) + kd) * C) * (p.w + 1) + (l_first + 1);
         for (int c0 = 0; c0 < C; c0 += kChunk) {
           const int nc = min(kChunk, C - c0);
-#pragma unroll 1
+#pragma unroll CU
           for (int cc = 0; cc < nc; ++cc) {
             const float4 q = col[(c0 + cc) * NDC];
             const float top = fmaf(lx, q.y, q.x), dif = fmaf(lx, q.w, q.z) - top;

@@ -85,12 +85,14 @@ class GraphedModel:
 
 
     def attack(self, keep_pred, early_stop, n_iter):
-        """The :class:`GraphedAttack` for this model / batch shape (cached)."""
-        key = (bool(keep_pred), bool(early_stop))
+        """The :class:`GraphedAttack` for this model / batch shape (cached).  The argmax map of the best
+        point is always tracked (8 B per pixel and iteration): apgd_largereps asks for it in its last stage
+        only, and one runner -- one set of static buffers and captured graphs -- then serves all stages."""
+        key = bool(early_stop)
         cache = self.__dict__.setdefault("_attacks", {})
         ga = cache.get(key)
         if ga is None or ga.n_iter_max < n_iter:
-            ga = cache[key] = GraphedAttack(self, keep_pred, early_stop, max(512, n_iter))
+            ga = cache[key] = GraphedAttack(self, True, early_stop, max(512, n_iter))
         return ga
 
 

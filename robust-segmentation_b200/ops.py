@@ -327,7 +327,7 @@ def project_linf(z, x, eps, noise=None, out=None):
         _f32c(z, "z")
     if noise is not None:
         _f32c(noise, "noise")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("project", 12 * x.numel()):
         rc = lib.robseg_project_linf(_ptr(z), x.data_ptr(), _ptr(noise), float(eps), x.numel(),
                                      out.data_ptr(), _stream())
     _lib.check(rc, "robseg_project_linf")
@@ -343,7 +343,7 @@ def pgd_step(X, delta, grad, alpha, eps, mask_outside=False, x_next=None, clamp_
         _f32c(t, n)
     if x_next is not None:
         _f32c(x_next, "x_next")
-    with torch.cuda.device(X.device):
+    with torch.cuda.device(X.device), _timed("pgd_step", (16 + (4 if x_next is not None else 0)) * X.numel()):
         rc = lib.robseg_pgd_step(X.data_ptr(), delta.data_ptr(), grad.data_ptr(), float(alpha),
                                  float(eps), int(mask_outside), int(clamp_next), X.numel(),
                                  _ptr(x_next), _stream())

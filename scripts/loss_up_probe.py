@@ -19,12 +19,14 @@ dbuf = torch.empty_like(up)
 dlow = torch.empty_like(low)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def timeit(fn, n=7):
+    """Median DEVICE time of the robseg launches inside fn (the wrappers' own CUDA events around each C call:
+    host-side gaps between launches are not counted)."""
     for _ in range(3): fn()
     ts = []
     for _ in range(n):
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        ops.profile_start(); fn(); torch.cuda.synchronize()
+        ts.append(sum(ms for _, _, ms in ops.profile_stop()))
     return statistics.median(ts)
 def three():
     u = ops._upsample_fwd(low, H, H)

@@ -93,7 +93,7 @@ def test_graphed_iteration_attack_matches_eager(mods, loss, n_iter, early):
     n_eager = mods.lib.launches - n0
     torch.manual_seed(5)
     xb, lb, ab, pb = mods.attacker.apgd_largereps(gm, x, y, w, **kw)
-    assert len(gm._attacks) == 1 and (loss, "ce-avg") in next(iter(gm._attacks.values())).graphs
+    assert len(gm._attacks) == 1 and (loss, "ce-avg") in next(iter(gm._attacks.values())).graphs  # one runner, 3 graphs
     # cuDNN may choose another data-gradient algorithm under capture: sign(grad) flips only where |grad| ~ 0
     assert float(((xa - xb).abs() > 1e-6).float().mean()) <= 0.02
     assert float((aa - ab).abs().max()) <= 3 / (S * S) + 1e-7

@@ -193,6 +193,42 @@ def test_loss_kernel_edge_cases(mods):
         o.loss_fwd_bwd(z, y, "ce")  # CPU tensors: no fallback
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_loss_kernel_full_size_vs_oracle(mods, dtype):
+    """One BASELINE config-2-shaped problem (2 x 150 x 512 x 512: the persistent TMA kernel's real tile
+    stream, VEC=2 rows) against the float64 oracle, fp32 and bf16: pred / correct / valid exact, loss
+    and gradient within BASELINE.json's 1e-5 (fp32) / 1e-2 (bf16)."""
+    B, C, H, W = 2, 150, 512, 512
+    z, y, w = make_problem(B, C, H, W, seed=5, bf16=dtype == "bf16")
+    zd = z.to(dev()) if dtype == "fp32" else z.to(dev()).bfloat16()
+    for kind in ("mask-ce-bal", "js-avg"):
+        out = mods.ops.loss_fwd_bwd(zd, y.to(dev()), kind, w.to(dev()), want_pred=True)
+        ref = O.loss_fwd_bwd(z.numpy().reshape(B, C, -1), y.numpy().reshape(B, -1), kind, w.numpy())
+        assert np.array_equal(out.pred.cpu().numpy().reshape(B, -1), ref["pred"])
+        assert np.array_equal(out.correct.cpu().numpy(), ref["correct"])
+        assert np.array_equal(out.valid.cpu().numpy(), ref["valid"])
+        assert rel(out.dlogits.float().cpu().numpy().reshape(B, C, -1), ref["dlogits"]) <= (1e-5 if dtype == "fp32" else 1e-2)
+        np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(out.track_img.cpu().numpy(), ref["track_img"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("C,H,W", [(21, 512, 512), (48, 128, 128), (64, 128, 160), (96, 64, 64)])
+def test_loss_kernel_bf16_wide_rows(mods, C, H, W):
+    """bf16 instantiations with 8 (C <= 48) and 4 (C <= 96) pixels per lane -- VOC's 21 classes at full
+    size among them -- against the oracle on bf16-representable logits."""
+    B = 2
+    z, y, w = make_problem(B, C, H, W, seed=C, bf16=True)
+    for kind in KINDS:
+        out = mods.ops.loss_fwd_bwd(z.to(dev()).bfloat16(), y.to(dev()), kind, w.to(dev()), want_pred=True)
+        ref = O.loss_fwd_bwd(z.numpy().reshape(B, C, -1), y.numpy().reshape(B, -1), kind, w.numpy())
+        assert np.array_equal(out.pred.cpu().numpy().reshape(B, -1), ref["pred"]), kind
+        assert np.array_equal(out.correct.cpu().numpy(), ref["correct"]), kind
+        assert rel(out.dlogits.float().cpu().numpy().reshape(B, C, -1), ref["dlogits"]) <= 1e-2, kind
+        np.testing.assert_allclose(out.loss_img.cpu().numpy(), ref["loss_img"], rtol=1e-5, atol=1e-8)
+        lo = mods.ops.loss_fwd_bwd(z.to(dev()).bfloat16(), y.to(dev()), kind, w.to(dev()), want_grad=False)
+        assert torch.equal(lo.loss_img, out.loss_img)
+
+
 def test_loss_kernel_properties_full_size(mods):
     """BASELINE config-2-sized tile stream (C=150, 512x512): size-independent properties."""
     o = mods.ops
@@ -482,8 +518,18 @@ def test_apgd_largereps_vs_reference_run(mods, golden, tag, kind):
         torch.rand_like = real_rand_like
     assert len(rec.inputs) == len(g["trace"])
     tr = torch.stack(rec.inputs).cpu().numpy()
+    # BASELINE.json's rule on this free-running trajectory: identical start, and the first update may
+    # differ only where the reference's |grad| is below 1e-5 of the image's max |grad| (afterwards the
+    # two trajectories feed on their own inputs; tests/test_gpu_e2e_rule.py teacher-forces EVERY
+    # recorded update of this fixture through the same rule, with zero tolerance elsewhere)
+    assert np.array_equal(tr[0], g["trace"][0])
+    B0 = g["x"].shape[0]
+    _, g0 = O._eval_point(O.TorchModelAdapter(_tiny(mods, g).cpu()), g["trace"][0], g["y"].reshape(B0, -1), kind,
+                          g["weights"], True)
+    gmax = np.abs(g0).reshape(B0, -1).max(1).reshape(-1, 1, 1, 1)
+    assert not ((tr[1] != g["trace"][1]) & (np.abs(g0) > 1e-5 * gmax)).any()
     bad = [(np.abs(tr[i] - g["trace"][i]) > 1e-6).mean() for i in range(len(tr))]
-    assert bad[0] <= 1e-3 and max(bad) <= 0.08, bad
+    assert bad[0] == 0 and bad[1] <= 1e-3 and max(bad) <= 0.08, bad
     P = g["y"][0].size
     assert np.abs(acc.cpu().numpy() - g["acc"]).max() <= 3.0 / P
     assert float((x_adv.cpu() - x).abs().max()) <= float(g["eps"]) + 1e-6

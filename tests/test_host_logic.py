@@ -338,6 +338,10 @@ def test_dropin_on_the_real_reference_copy(mods, monkeypatch):
         assert import_module("semseg.models").UperNetForSemanticSegmentation is TI.UperNetForSemanticSegmentation.__wrapped__
         with pytest.raises(SystemExit):  # the reference's argparse, reached through ITS main block
             dropin.run_infer_main(["--help"])
+        # the PIR-AT trainer (tools/train_rob_seg.py:19,22,33) binds the B200 attack / losses at import time
+        TR = import_module("tools.train_rob_seg")
+        assert TR.Pgd_Attack is mods.val.Pgd_Attack and TR.evaluate is mods.val.evaluate
+        assert TR.attacker is mods.attacker and TR.get_loss is import_module("robseg_b200.semseg.losses").get_loss
     finally:
         dropin.uninstall()
     for n, v in theirs.items():
