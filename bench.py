@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--reforward", action="store_true",
                     help="re-forward every adversarial batch for its argmax map like tools/infer.py "
                          "(default: the attack returns it, SURVEY 8f-2)")
+    ap.add_argument("--pred-maps", action="store_true",
+                    help="score the adversarial points from int64 argmax maps + robseg_pixel_hist (round-1 flow) "
+                         "instead of the counters fused into the loss kernel (robseg_loss_fwd_bwd_counts)")
     ap.add_argument("--stock-upsample", action="store_true",
                     help="keep F.interpolate for every bilinear up-sampling of the consumer (default: robseg kernels)")
     ap.add_argument("--logit-upsample-only", action="store_true",
@@ -151,7 +154,7 @@ def sea_step(mods, model, x, y, w, args, world, e2e_host=None):
         x = e2e_host[0].to(x.device, non_blocking=True)
         y = e2e_host[1].to(y.device, non_blocking=True)
     B, C = x.shape[0], args.classes
-    preds = []
+    preds, counts = [], []
     x_advs = []
     for loss in LOSSES:
         if args.reforward:  # the reference's flow: re-forward every adversarial batch (tools/infer.py:82-90)
@@ -161,19 +164,28 @@ def sea_step(mods, model, x, y, w, args, world, e2e_host=None):
             with torch.no_grad():
                 out = model(x_adv)
             pred = ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred
-        else:  # the attack hands back the argmax map of its adversarial point
+        elif args.pred_maps:  # the attack hands back the argmax map of its adversarial point
             x_adv, _, acc, pred = att.apgd_largereps(
                 model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
                 track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C, return_pred=True)
+        else:  # ... or directly the per-image class counters of that point, taken in the loss kernel's argmax pass
+            x_adv, _, acc, cnt = att.apgd_largereps(
+                model, x, y, w, norm="Linf", eps=args.eps / 255.0, n_iter=args.n_iter, loss=loss,
+                track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=C, return_counts=True)
+            counts.append(cnt)
+            pred = None
         preds.append(pred)
         x_advs.append(x_adv)
-    cnt = ops.pixel_hist(torch.stack(preds).flatten(0, 1), y, C)
-    inter, tgt, prd = (cnt[k].view(len(LOSSES), B, C) for k in ("inter", "tgt", "prd"))
+    if counts:
+        inter, tgt, prd = (torch.stack(counts)[:, :, k].contiguous() for k in range(3))  # each [A,B,C]
+    else:
+        cnt = ops.pixel_hist(torch.stack(preds).flatten(0, 1), y, C)
+        inter, tgt, prd = (cnt[k].view(len(LOSSES), B, C) for k in ("inter", "tgt", "prd"))
     rank = int(os.environ.get("RANK", 0))
     gi, gt, gp, _ = dist_mod.allreduce_counters(B * world, rank * B, inter, tgt, prd)
     acc_an, worst = ops.sea_worst_acc(gi, gt)
     if e2e_host is not None:  # results back to pinned host memory (tools/infer.py:151 keeps every x_adv)
-        if "out" not in _PINNED:
+        if "out" not in _PINNED:  # (run_ours allocates these before the timed region: pinning 150 MB takes ~0.1 s)
             _PINNED["out"] = [torch.empty(xa.shape, dtype=xa.dtype).pin_memory() for xa in x_advs]
             _PINNED["worst"] = torch.empty(worst.shape, dtype=worst.dtype).pin_memory()
         for h, xa in zip(_PINNED["out"], x_advs):
@@ -234,44 +246,56 @@ def build_consumer(args, mods, dev, accelerated=True):
     return model.to(dev).eval(), "consumers.py look-alike (%s), random init" % type(model).__name__
 
 
-def fused_variant(args, mods, dev, x, y, w, world, iters_per_step):
-    """The same step with the x4 logit up-sampling fused into the loss kernel (--fuse-loss): one warm-up,
-    one timed step.  Reported beside the default so the x4 decision rests on driver-visible numbers."""
+def variant_step(args, mods, dev, x, y, w, world, iters_per_step, fuse=False, graph=False):
+    """The same step in another configuration, one warm-up (two with --graph: capture) and one timed step, reported
+    beside the default so the decision rests on driver-visible numbers: `fuse` = the x4 logit up-sampling fused into
+    the loss kernel (--fuse-loss), `graph` = one CUDA graph per APGD iteration (--graph)."""
     import torch
 
     try:
         saved = args.fuse_loss
-        args.fuse_loss = True
+        args.fuse_loss = bool(fuse)
         model, _ = build_consumer(args, mods, dev)
         args.fuse_loss = saved
         for p in model.parameters():
             p.requires_grad_(True)
-        if not hasattr(model, "forward_lowres"):
+        if fuse and not hasattr(model, "forward_lowres"):
             return {"unavailable": "consumer offers no forward_lowres"}
-        torch.manual_seed(1234)
-        sea_step(mods, model, x, y, w, args, world)
+        if graph:
+            model = mods["graphs"].GraphedModel(model, x)
+        for _ in range(2 if graph else 1):
+            torch.manual_seed(1234)
+            sea_step(mods, model, x, y, w, args, world)
         torch.cuda.synchronize()
         torch.cuda.reset_peak_memory_stats(dev)
-        mods["ops"].profile_start()
+        launches0 = mods["lib"].launches
+        if not graph:  # (launches inside a replayed graph are not seen by the wrappers' events)
+            mods["ops"].profile_start()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.manual_seed(1234)
         t0.record()
         sea_step(mods, model, x, y, w, args, world)
         t1.record()
         torch.cuda.synchronize()
-        prof = mods["ops"].profile_stop()
+        prof = mods["ops"].profile_stop() if not graph else []
         ms = t0.elapsed_time(t1)
         by = {}
         for name, _, t in prof:
             by[name] = by.get(name, 0.0) + t
+        res = {"value": round(iters_per_step / (ms / 1e3), 3), "unit": UNIT, "ms_per_step": round(ms, 1),
+               "peak_mem_GiB": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1), "steps": 1,
+               "warmup": 2 if graph else 1, "host_launch_calls": mods["lib"].launches - launches0}
+        if by:
+            res["attack_side_ms_per_step"] = round(sum(by.values()), 3)
+            res["kernels_ms_per_step"] = {k: round(v, 3) for k, v in by.items()}
+        res["what"] = ("one CUDA graph per APGD iteration (graphs.GraphedAttack: step + forward + loss + input-gradient "
+                       "backward + bookkeeping), the early-stop flag polled one iteration late" if graph else
+                       "robseg_loss_upsampled_fwd_bwd: the [B,C,512,512] logits / dlogits never exist")
         del model
         torch.cuda.empty_cache()
-        return {"value": round(iters_per_step / (ms / 1e3), 3), "unit": UNIT, "ms_per_step": round(ms, 1),
-                "attack_side_ms_per_step": round(sum(by.values()), 3),
-                "kernels_ms_per_step": {k: round(v, 3) for k, v in by.items()},
-                "peak_mem_GiB": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1), "steps": 1, "warmup": 1,
-                "what": "robseg_loss_upsampled_fwd_bwd: the [B,C,512,512] logits / dlogits never exist"}
+        return res
     except Exception as e:
+        torch.cuda.empty_cache()
         return {"unavailable": repr(e)[:200]}
 
 
@@ -388,9 +412,11 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), keep
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         torch.manual_seed(1234)
-        sea_step(mods, model, x, y, w, args, world)
+        # the last warm-up step goes through the host-buffer path once: it allocates (pins) the result buffers
+        # of the e2e arm, a one-off ~0.1 s of cudaHostAlloc that is not part of a step
+        sea_step(mods, model, x, y, w, args, world, (hx, hy) if i == args.warmup - 1 else None)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -424,8 +450,6 @@ def run_ours(args):
         d[0] += nbytes
         d[1] += t
         d[2] += 1
-    lg = by.get("loss_grad", [0, 1e-9, 1])
-    achieved = lg[0] / (lg[1] / 1e3) / 1e9
     ours_ms = sum(v[1] for v in by.values())
     h2d = B * 3 * S * S * 4 + B * S * S * 8
     d2h = len(LOSSES) * B * 3 * S * S * 4 + B * world * 4
@@ -445,7 +469,9 @@ def run_ours(args):
             "model_fwd_per_step": len(LOSSES) * (args.n_iter + 3 + (1 if args.reforward else 0)),
             "model_bwd_per_step": len(LOSSES) * args.n_iter,
             "adversarial_argmax": "re-forward of x_adv (tools/infer.py:82-90)" if args.reforward else
-            "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)",
+            "returned by the attack (return_pred=True, SURVEY 8f-2; --reforward restores the re-forward)" if args.pred_maps
+            else "never materialised: the attack returns the per-image class counters of its adversarial point, taken in "
+                 "the loss kernel's argmax pass (return_counts=True; --pred-maps / --reforward restore the earlier flows)",
             "consumer_model": consumer_desc,
             "peak_mem_GiB": round(peak_gib, 1),
             "final_logit_upsampling": ("fused into the loss kernel (robseg_loss_upsampled_fwd_bwd): the [B,C,H,W] "
@@ -470,17 +496,15 @@ def run_ours(args):
         "e2e": {"value": round(value_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
-                     "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s",
-                     "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C),
-                     "peak_source": peaks[1], "launches_timed": lg[2],
-                     "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
-                     "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
+        "roofline": sea_roofline(by, B, C, S, peaks, clocks),
     }
     if world == 1 and args.model == "upernet" and not args.fuse_loss and not args.graph and upsample_mode(args):
-        line["config"]["fused_x4_variant"] = fused_variant(args, mods, dev, x, y, w, world, iters_per_step)
+        del model
+        torch.cuda.empty_cache()
+        line["config"]["fused_x4_variant"] = variant_step(args, mods, dev, x, y, w, world, iters_per_step, fuse=True)
+        line["config"]["graph_variant"] = variant_step(args, mods, dev, x, y, w, world, iters_per_step, graph=True)
     if world == 1 and not args.no_ref_on_gpu:
-        del model, keep, keep_e2e
+        model = keep = keep_e2e = None
         torch.cuda.empty_cache()
         line["config"]["reference_on_gpu"] = reference_on_gpu(args, mods, dev, x, y, w)
         r = line["config"]["reference_on_gpu"].get("value")
@@ -493,6 +517,34 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sea_roofline(by, B, C, S, peaks, clocks):
+    """`roofline` of the dominant robseg kernel of a SEA step, from the per-launch CUDA events of the timed region.
+    Default step: loss_tma_kernel (HBM-bound, algorithmic bytes = logits in + gradient out + labels).  With the final
+    up-sampling fused into the loss (SegMenter default, --fuse-loss) the [B,C,H,W] tensors never exist: that kernel moves
+    1/R^2 of the bytes and is bound by the ex2 pipe (2 ex2 per up-sampled logit, 16 lanes / clk / SM), so its HBM
+    fraction is small BY DESIGN; the ex2-pipe fraction is reported beside it."""
+    if "loss_grad" in by:
+        lg = by["loss_grad"]
+        achieved = lg[0] / (lg[1] / 1e3) / 1e9
+        return {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
+                "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s", "frac": round(achieved / peaks[0], 4),
+                "traffic": load_traffic("sea_c%d" % C), "peak_source": peaks[1], "launches_timed": lg[2],
+                "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4), "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)}
+    lg = by.get("loss_up_grad", [0, 1e-9, 1])
+    achieved = lg[0] / (lg[1] / 1e3) / 1e9
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    ex2_peak = 16 * 148 * mhz * 1e6  # MUFU.EX2 lanes per second (B300_MICROARCH: 16 / clk / SM)
+    ex2_rate = 2.0 * B * C * S * S * lg[2] / (lg[1] / 1e3)  # pass 2 + pass 3: two ex2 per up-sampled logit
+    return {"bound": "hbm", "kernel": "loss_up_kernel<R> (loss taken through the bilinear up-sampling, C=%d)" % C,
+            "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s", "frac": round(achieved / peaks[0], 4),
+            "traffic": load_traffic("sea_up_c%d" % C), "peak_source": peaks[1], "launches_timed": lg[2],
+            "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4), "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1),
+            "note": "not HBM-bound by construction (the [B,C,H,W] logits / gradient never exist): limited by the ex2 pipe",
+            "ex2_pipe": {"achieved_Gex2_per_s": round(ex2_rate / 1e9, 1), "peak_Gex2_per_s": round(ex2_peak / 1e9, 1),
+                         "frac": round(ex2_rate / ex2_peak, 4)},
+            "unfused_equivalent_GBps": round((2 * B * C * S * S * 4 + 8 * B * S * S) * lg[2] / (lg[1] / 1e3) / 1e9, 1)}
 
 
 def loss_kernel_probe(mods, dev, B, C, S, reps=5):
@@ -769,6 +821,13 @@ def run_micro(args, mods, dev, rank, world):
             z.numel() * es + 8 * y.numel())
     time_it("argmax", lambda: ops.loss_fwd_bwd(z, y, "argmax", want_grad=False, want_pred=True, want_stats=False),
             z.numel() * es + 16 * y.numel())
+    # the per-image class counters taken in the same pass (robseg_loss_fwd_bwd_counts): uniformly random labels are
+    # the worst case for the warp-aggregated reductions (one per lane), coherent maps the normal one (one per warp row)
+    time_it("loss_grad+counts/mask-ce-avg uniform-random", lambda: ops.loss_fwd_bwd(z, y, "mask-ce-avg", w, dlogits_out=dbuf,
+                                                                                      want_counts=True),
+            2 * z.numel() * es + 8 * y.numel())
+    time_it("argmax+counts uniform-random", lambda: ops.loss_fwd_bwd(z, y, "argmax", want_grad=False, want_stats=False,
+                                                                      want_counts=True), z.numel() * es + 8 * y.numel())
     time_it("apgd_step", lambda: ops.apgd_step(x, xa, xo, gr, step, 8 / 255, 0.75, xn), 20 * x.numel(), "apgd_step")
     pred = z.argmax(1)
     time_it("pixel_hist/counts uniform-random", lambda: ops.pixel_hist(pred, y, C), 16 * y.numel(), "pixel_hist")
@@ -777,11 +836,23 @@ def run_micro(args, mods, dev, rank, world):
     ys = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.8, torch.full_like(y, 3), y)  # 80 % one class
     ps = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.7, ys, pred)
     time_it("pixel_hist/counts skewed-80pct", lambda: ops.pixel_hist(ps, ys, C), 16 * y.numel(), "pixel_hist")
-    blk = torch.randint(0, C, (B, S // 64, S // 64), device=dev, generator=g)  # 64x64 constant regions
-    yc = blk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()
+    nb = (S + 63) // 64
+    blk = torch.randint(0, C, (B, nb, nb), device=dev, generator=g)  # 64x64 constant regions
+    yc = blk.repeat_interleave(64, 1).repeat_interleave(64, 2)[:, :S, :S].contiguous()
     pblk = torch.where(torch.rand(blk.shape, device=dev, generator=g) < 0.7, blk, torch.randint_like(blk, C))
-    pc = pblk.repeat_interleave(64, 1).repeat_interleave(64, 2).contiguous()  # region-wise right / wrong
+    pc = pblk.repeat_interleave(64, 1).repeat_interleave(64, 2)[:, :S, :S].contiguous()  # region-wise right / wrong
     time_it("pixel_hist/counts piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C), 16 * y.numel(), "pixel_hist")
+    time_it("loss_grad+counts/mask-ce-avg piecewise-constant-64x64 labels, random predictions",
+            lambda: ops.loss_fwd_bwd(z, yc, "mask-ce-avg", w, dlogits_out=dbuf, want_counts=True),
+            2 * z.numel() * es + 8 * y.numel())
+    # the realistic case: labels AND predictions spatially coherent (argmax = pc: region-wise right / wrong)
+    z.scatter_add_(1, pc.unsqueeze(1), torch.full((B, 1, S, S), 30.0, device=dev, dtype=dt))
+    time_it("loss_grad/mask-ce-avg coherent labels and predictions",
+            lambda: ops.loss_fwd_bwd(z, yc, "mask-ce-avg", w, dlogits_out=dbuf), 2 * z.numel() * es + 8 * y.numel())
+    time_it("loss_grad+counts/mask-ce-avg coherent labels and predictions",
+            lambda: ops.loss_fwd_bwd(z, yc, "mask-ce-avg", w, dlogits_out=dbuf, want_counts=True),
+            2 * z.numel() * es + 8 * y.numel())
+    z.scatter_add_(1, pc.unsqueeze(1), torch.full((B, 1, S, S), -30.0, device=dev, dtype=dt))
     time_it("pixel_hist/full piecewise-constant-64x64", lambda: ops.pixel_hist(pc, yc, C, want_hist=True, want_counts=False),
             16 * y.numel(), "pixel_hist")
     if args.micro_dtype == "fp32":

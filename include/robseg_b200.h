@@ -113,6 +113,32 @@ int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* labels, const
                                   robseg_stream_t stream);
 
 /*
+ * The two fused-loss calls with the per-image class counters of compute_iou_acc
+ * (semseg/attacker.py:9-52, called on every iteration's argmax at :496-498; the same counters
+ * tools/infer.py:86-116 and evalSEA, tools/worse_only.py:30-66, derive from a prediction map) taken
+ * in the kernel's argmax pass, so neither the int64 prediction map nor a robseg_pixel_hist launch
+ * is needed to score an adversarial point:
+ *   counts [B,3,C] int64 (zeroed by the call):  [b,0,c] = #{pred == label == c},
+ *   [b,1,c] = #{label == c}, [b,2,c] = #{pred == c, label valid}; ignored pixels add nothing.
+ * Exact (integer reductions), identical to robseg_pixel_hist on the pred this call would return.
+ * All other arguments as in robseg_loss_fwd_bwd / robseg_loss_upsampled_fwd_bwd.
+ */
+int robseg_loss_fwd_bwd_counts(const void* logits, int dtype, const int64_t* labels,
+                               const float* class_w, int loss_kind, int ignore_index, int B, int C,
+                               int64_t HW, const float* grad_scale, const float* upstream_pix,
+                               void* dlogits, float* loss_pix, int64_t* pred, float* loss_img,
+                               float* track_img, int32_t* correct_img, int32_t* valid_img,
+                               int64_t* counts, void* workspace, size_t workspace_bytes,
+                               robseg_stream_t stream);
+int robseg_loss_upsampled_fwd_bwd_counts(const float* low, const int64_t* labels, const float* class_w,
+                                         int loss_kind, int ignore_index, int B, int C, int h, int w,
+                                         int H, int W, const float* grad_scale, float* dlow,
+                                         int64_t* pred, float* loss_img, float* track_img,
+                                         int32_t* correct_img, int32_t* valid_img, int64_t* counts,
+                                         void* workspace, size_t workspace_bytes,
+                                         robseg_stream_t stream);
+
+/*
  * One L-inf APGD update for the whole batch, bit-exact with the fp32 op chain of
  * semseg/attacker.py:388-410:
  *   g2 = x_adv - x_old

@@ -30,9 +30,13 @@ SIGNATURES = {
     "robseg_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i]),
     "robseg_loss_fwd_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _sz, _p]),
+    "robseg_loss_fwd_bwd_counts": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p,
+                                        _p, _p, _p, _p, _p, _sz, _p]),
     "robseg_loss_upsampled_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "robseg_loss_upsampled_fwd_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p,
                                            _p, _p, _sz, _p]),
+    "robseg_loss_upsampled_fwd_bwd_counts": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p,
+                                                  _p, _p, _p, _p, _sz, _p]),
     "robseg_apgd_step": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p]),
     "robseg_apgd_step_fused": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _i, _i64, _p, _p, _p, _p, _p, _p]),
     "robseg_apgd_step_ctl": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _p, _p, _p, _p, _p]),

@@ -93,6 +93,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Per-image class counters folded into the loss kernels' argmax pass (compute_iou_acc, semseg/attacker.py:9-52;
+// the same counters robseg_pixel_hist returns): cnt = this image's [3][C] int64 block
+// (intersection, target, prediction), updated with 64-bit reductions that return nothing (RED.E.ADD.64): integer,
+// hence exact and order-independent.  Aggregation per warp row WITHOUT warp-match instructions (MATCH.ANY on 32
+// distinct keys cost ~19 % of the loss kernel on uniformly random labels): twice, the first still-uncounted lane
+// announces its class, every lane holding the same class is counted by that one lane (ballot + popc, one
+// reduction); whatever is left after two rounds -- nothing on a coherent map, nothing on a two-class boundary row --
+// issues its own reduction.  A pixel whose label is ignored contributes nothing (its prediction is ignored too,
+// attacker.py:20).  Must be called by all 32 lanes.
+__device__ __forceinline__ void count_keys(unsigned long long* arr, bool valid, int key) {
+  const int lane = threadIdx.x & 31;
+  unsigned left = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (left == 0u) return;  // warp-uniform
+    const int first = __ffs(left) - 1;
+    const int k0 = __shfl_sync(0xffffffffu, key, first);
+    const unsigned same = __ballot_sync(0xffffffffu, valid && key == k0) & left;
+    if (lane == first) atomicAdd(arr + k0, (unsigned long long)__popc(same));
+    left &= ~same;
+  }
+  if ((left >> lane) & 1u) atomicAdd(arr + key, 1ull);
+}
+__device__ __forceinline__ void count_pixel(unsigned long long* cnt, int C, bool valid, int t, int q) {
+  count_keys(cnt + C, valid, t);              // target
+  count_keys(cnt + 2 * C, valid, q);          // prediction (only where the label is valid)
+  count_keys(cnt, valid && t == q, t);        // intersection
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

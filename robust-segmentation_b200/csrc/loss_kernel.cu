@@ -42,6 +42,7 @@ struct LossParams {
   float* loss_pix;
   int64_t* pred;
   float4* partials;
+  unsigned long long* counts;  // [B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
   int64_t HW;
   int kind, ignore_index, B, C;
   int tiles_per_img, num_tiles, n_slots, n_consumers;
@@ -150,12 +151,75 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // alignment requirement and a lane may be only partly inside the image.  The stage is still
 // lane-major (pixel lane+32j at column lane*VEC+j: the 4-byte fill transposes), so shared memory
 // is read with one vector load per row in both modes.
-template <typename T, int VEC, int G, bool PARTIAL, bool STR = false>
-__device__ __forceinline__ void process_tile(const LossParams& p, const T* __restrict__ tile,
-                                             int tile_idx, int lane, int half,
-                                             const PairXch& xch) {
-  static_assert(!STR || G == 1, "strided pixels: one warp per stage");
+//
+// bf16 with gradient (KEEP_E): pass 2 leaves e = 2^(z*log2e - mL), rounded to bf16, IN the stage (the warp
+// owns it until it releases it), and pass 3 is one packed multiply per pair of logits (HMUL2.BF16) instead
+// of unpack - FMA - ex2 - multiply - pack: the bf16 kernel was instruction-bound at 83 % of the roofline
+// (19.7 instructions per logit, profiles/r01b_ncu_loss_bf16.md).  The gradient then carries three bf16
+// roundings (e, coef/s, the product) instead of one: <= 0.6 % relative, inside the 1e-2 bf16 tolerance.
+// (label, argmax) of a lane's VEC pixels, t = -1 where the label is ignored / out of range / beyond the image:
+// what the per-image class counters (LossParams::counts) are updated from.  The TMA consumers count a tile while
+// the NEXT one is being processed: the reductions are then long complete when the warp releases a stage
+// (mbarrier.arrive has release semantics and would otherwise wait for their round trip to L2 once per tile --
+// measured +19 % on the loss kernel with uniformly random labels when they were issued at the end of the tile).
+template <int VEC>
+struct TileCls {
+  int t[VEC], q[VEC];
+  int b;
+};
+template <int VEC>
+__device__ __forceinline__ void count_tile(const LossParams& p, const TileCls<VEC>& k) {
+  unsigned long long* cnt = p.counts + (size_t)k.b * 3 * p.C;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) count_pixel(cnt, p.C, k.t[j] >= 0, k.t[j], k.q[j]);
+}
+
+// The labels of a warp tile (int64 -> int), ignore_index for pixels beyond the image.  Separate from
+// process_tile so that the TMA consumers can issue these loads BEFORE they wait for their stage: the
+// label latency then overlaps the wait instead of sitting between pass 1 and the first use.
+template <int VEC, bool PARTIAL, bool STR>
+__device__ __forceinline__ void tile_labels(const LossParams& p, int tile_idx, int lane, int (&y)[VEC]) {
   constexpr int ROW = 32 * VEC;
+  constexpr int PS = STR ? 32 : 1;
+  const int b = tile_idx / p.tiles_per_img;
+  const int64_t px = (int64_t)(tile_idx - b * p.tiles_per_img) * ROW + (STR ? lane : lane * VEC);
+  const int64_t pix = (int64_t)b * p.HW + px;
+  const bool inb = PARTIAL ? (px < p.HW) : true;
+  if constexpr (STR) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      y[j] = (!PARTIAL || px + j * PS < p.HW) ? (int)__ldg(p.labels + pix + j * PS) : p.ignore_index;
+  } else if (inb) {
+    if constexpr (VEC == 1) {
+      y[0] = (int)__ldg(p.labels + pix);
+    } else {
+      const longlong2* lp = reinterpret_cast<const longlong2*>(p.labels + pix);
+#pragma unroll
+      for (int j = 0; j < VEC / 2; ++j) {
+        longlong2 t = __ldg(lp + j);
+        y[2 * j] = (int)t.x, y[2 * j + 1] = (int)t.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) y[j] = p.ignore_index;
+  }
+}
+
+//
+// OVF (generic path, fp32, with STR): the stage holds every channel row as the ALIGNED 16-byte chunks that
+// cover the tile's pixels -- rows of ROW + 4 floats filled with 16-byte cp.async copies -- so pixel i of row c
+// sits at column phase(c) + i, phase(c) = (ph0 + c * (HW & 3)) & 3.  Rows c, c+4, c+8, ... share their phase,
+// so the unrolled loops (which start at multiples of 4) use four precomputed offsets; shared memory is read
+// with conflict-free scalar loads (lane + 32 j).
+template <typename T, int VEC, int G, bool PARTIAL, bool STR = false, bool OVF = false>
+__device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int tile_idx, int lane, int half,
+                                             const PairXch& xch, const int (&y)[VEC], TileCls<VEC>* cls = nullptr,
+                                             int ph0 = 0) {
+  static_assert(!STR || G == 1, "strided pixels: one warp per stage");
+  static_assert(!OVF || (STR && sizeof(T) == 4), "over-fetched rows: fp32, strided pixel ownership");
+  constexpr int ROW = 32 * VEC;
+  constexpr int RS = OVF ? ROW + 4 : ROW;  // row stride of the stage in elements
   constexpr int PS = STR ? 32 : 1;  // distance between the lane's pixels
   constexpr int NACC = (VEC >= 4) ? 1 : 4 / VEC;  // independent accumulator sets per pixel
   constexpr int UNR = 8;
@@ -172,11 +236,30 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
   for (int j = 0; j < VEC; ++j) inj[j] = (STR && PARTIAL) ? (px + j * PS < p.HW) : inb;
   const int64_t pix = (int64_t)b * p.HW + px;
-  // shared memory is lane-major in both modes (the strided fill transposes): one vector load per row
-  const T* col = tile + lane * VEC;
+  // shared memory is lane-major in both dense modes (the strided fill transposes): one vector load per row
+  T* col = OVF ? tile + lane : tile + lane * VEC;
+  int phs[4] = {0, 0, 0, 0};
+  const int dph = OVF ? (int)(p.HW & 3) : 0;
+  if constexpr (OVF) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) phs[q] = (ph0 + q * dph) & 3;
+  }
+  // row c of the stage -> the lane's VEC logits.  `slot` = c & 3 where the caller knows it at compile time
+  // (unrolled trips that start at a multiple of 4), -1 otherwise.
+  auto ldrow = [&](int c, int slot, float (&v)[VEC]) {
+    if constexpr (OVF) {
+      const int ph = slot >= 0 ? phs[slot & 3] : ((ph0 + c * dph) & 3);
+      const float* rp = reinterpret_cast<const float*>(col) + c * RS + ph;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = rp[32 * j];
+    } else {
+      Vec<T, VEC>::lds(col + c * ROW, v);
+    }
+  };
   const bool argmax_only = p.kind == ROBSEG_LOSS_ARGMAX;
+  constexpr bool KEEP_E = sizeof(T) == 2 && VEC >= 2 && !STR;
+  const bool keep_e = KEEP_E && p.dlogits != nullptr;
   using V = Vec<T, VEC>;
-  auto ldsv = [&](const T* q, float (&v)[VEC]) { V::lds(q, v); };
   auto stgv = [&](T* q, const float (&v)[VEC]) {
     if constexpr (STR) {
 #pragma unroll
@@ -189,27 +272,6 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       if (inb) V::stg(q, v);
     }
   };
-
-  // labels: issued now, consumed after pass 1
-  int y[VEC];
-  if constexpr (STR) {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) y[j] = inj[j] ? (int)__ldg(p.labels + pix + j * PS) : p.ignore_index;
-  } else if (inb) {
-    if constexpr (VEC == 1) {
-      y[0] = (int)__ldg(p.labels + pix);
-    } else {
-      const longlong2* lp = reinterpret_cast<const longlong2*>(p.labels + pix);
-#pragma unroll
-      for (int j = 0; j < VEC / 2; ++j) {
-        longlong2 t = __ldg(lp + j);
-        y[2 * j] = (int)t.x, y[2 * j + 1] = (int)t.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) y[j] = p.ignore_index;
-  }
 
   // ---- pass 1: channel max.  ARGMAX-only launches also track the index here (one pass);
   // loss launches find the first maximal channel by equality during pass 2.
@@ -228,7 +290,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         float v[VEC];
-        ldsv(col + (c + u) * ROW, v);
+        ldrow(c + u, u, v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           const bool g = v[j] > m[u % NACC][j];
@@ -240,7 +302,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll 1
     for (; c < c_hi; ++c) {
       float v[VEC];
-      ldsv(col + c * ROW, v);
+      ldrow(c, -1, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const bool g = v[j] > m[0][j] || (v[j] == m[0][j] && c < am[0][j]);
@@ -319,17 +381,29 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll
       for (int u = 0; u < UNR; u += 2) {
         float v0[VEC], v1[VEC];
-        ldsv(col + (c + u) * ROW, v0);
-        ldsv(col + (c + u + 1) * ROW, v1);
+        ldrow(c + u, u, v0);
+        ldrow(c + u + 1, u + 1, v1);
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
           m[(u / 2) % NACC][j] = fmax3(m[(u / 2) % NACC][j], v0[j], v1[j]);
       }
     }
+    if (c + 4 <= c_hi) {  // a half trip keeps the scalar tail below 4 rows (C = 21: 16 + 4 + 1)
+#pragma unroll
+      for (int u = 0; u < 4; u += 2) {
+        float v0[VEC], v1[VEC];
+        ldrow(c + u, u, v0);
+        ldrow(c + u + 1, u + 1, v1);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          m[(u / 2) % NACC][j] = fmax3(m[(u / 2) % NACC][j], v0[j], v1[j]);
+      }
+      c += 4;
+    }
 #pragma unroll 1
     for (; c < c_hi; ++c) {
       float v[VEC];
-      ldsv(col + c * ROW, v);
+      ldrow(c, -1, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) m[0][j] = fmaxf(m[0][j], v[j]);
     }
@@ -383,34 +457,98 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       mL[j] = mx[j] * kLog2e;
       resid[j] = fmaf(mx[j], kLog2e, -mL[j]);
     }
+    // the label logit: read before pass 2 overwrites the stage (KEEP_E); otherwise after it, when the
+    // labels have certainly arrived
+    float zyv[VEC];
+    if (keep_e) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const bool v = inj[j] && (y[j] != p.ignore_index) && (y[j] >= 0) && (y[j] < C);
+        zyv[j] = V::ld1(col + (v ? y[j] : 0) * ROW + j);
+      }
+      if constexpr (G == 2) pair_sync(xch.bar_id);  // the partner reads label logits from MY channel half too
+    }
     float s[NACC][VEC];
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) s[a][j] = 0.f;
+    // e values of one row back into the stage as packed bf16 (KEEP_E only)
+    auto put_e = [&](T* q, const float (&e)[VEC]) {
+      if constexpr (KEEP_E) {
+        using VB = Vec<__nv_bfloat16, VEC>;
+        if constexpr (VEC == 2) {
+          *reinterpret_cast<uint32_t*>(q) = VB::pack(e[0], e[1]);
+        } else if constexpr (VEC == 4) {
+          *reinterpret_cast<uint2*>(q) = make_uint2(VB::pack(e[0], e[1]), VB::pack(e[2], e[3]));
+        } else {
+          *reinterpret_cast<uint4*>(q) = make_uint4(VB::pack(e[0], e[1]), VB::pack(e[2], e[3]),
+                                                    VB::pack(e[4], e[5]), VB::pack(e[6], e[7]));
+        }
+      }
+    };
     int c = c_hi;
+    // one half trip of 4 rows (rows c-1 .. c-4), walking downwards like the full trips
+    auto half_trip = [&]() {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[VEC], e[VEC];
+        ldrow(c - 1 - u, OVF ? (3 - u) : -1, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          e[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+          s[u % NACC][j] += e[j];
+          if (v[j] == mx[j]) amx[j] = c - 1 - u;
+        }
+        if (keep_e) put_e(col + (c - 1 - u) * ROW, e);
+      }
+      c -= 4;
+    };
+    if constexpr (OVF) {
+      // the rows above the last multiple of 4 first (still walking downwards), then a half trip down to a
+      // multiple of UNR, so that every unrolled trip starts at a multiple of 4 and knows its rows' phases at
+      // compile time
+#pragma unroll 1
+      for (; c > c_lo && (c & 3) != 0; --c) {
+        float v[VEC];
+        ldrow(c - 1, -1, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+          if (v[j] == mx[j]) amx[j] = c - 1;
+        }
+      }
+      if ((c & 4) != 0 && c - 4 >= c_lo) half_trip();
+    }
 #pragma unroll 1
     for (; c - UNR >= c_lo; c -= UNR) {
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        float v[VEC];
-        ldsv(col + (c - 1 - u) * ROW, v);
+        float v[VEC], e[VEC];
+        ldrow(c - 1 - u, OVF ? (UNR - 1 - u) : -1, v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          s[u % NACC][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+          e[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+          s[u % NACC][j] += e[j];
           if (v[j] == mx[j]) amx[j] = c - 1 - u;
         }
+        if (keep_e) put_e(col + (c - 1 - u) * ROW, e);
       }
+    }
+    if constexpr (!OVF) {
+      if (c - 4 >= c_lo) half_trip();
     }
 #pragma unroll 1
     for (; c > c_lo; --c) {
-      float v[VEC];
-      ldsv(col + (c - 1) * ROW, v);
+      float v[VEC], e[VEC];
+      ldrow(c - 1, -1, v);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        s[0][j] += ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+        e[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j]));
+        s[0][j] += e[j];
         if (v[j] == mx[j]) amx[j] = c - 1;
       }
+      if (keep_e) put_e(col + (c - 1) * ROW, e);
     }
     float st[VEC];
 #pragma unroll
@@ -446,7 +584,9 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
       hit[j] = valid[j] && (amx[j] == y[j]);
       ys[j] = valid[j] ? y[j] : 0;
       n_correct += hit[j], n_valid += valid[j];
-      const float zy = V::ld1(col + ys[j] * ROW + j);
+      float zy;
+      if constexpr (OVF) zy = reinterpret_cast<const float*>(col)[ys[j] * RS + ((ph0 + ys[j] * dph) & 3) + 32 * j];
+      else zy = keep_e ? zyv[j] : V::ld1(col + ys[j] * ROW + j);
       const float ln_s = logf(st[j]) - resid[j] * kLn2;  // lse - m
       const float logp = (zy - mx[j]) - ln_s;            // log softmax_y  (<= 0)
       const float ce = valid[j] ? -logp : 0.f;
@@ -506,13 +646,51 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
 #pragma unroll 4
           for (c = c_lo; c < c_hi; ++c, gp += hw) stgv(gp, zero);
         }
+      } else if (KEEP_E) {
+        if constexpr (KEEP_E) {
+          // the stage holds e (bf16): gradient = e * (coef / s), one packed multiply per pair
+          constexpr int NW = VEC / 2;
+          __nv_bfloat162 k2[NW];
+#pragma unroll
+          for (int k = 0; k < NW; ++k) k2[k] = __floats2bfloat162_rn(kfac[2 * k], kfac[2 * k + 1]);
+          auto mul_store = [&](const T* q, T* g) {
+            if constexpr (NW == 1) {
+              const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(q), k2[0]);
+              if (inb) __stcs(reinterpret_cast<uint32_t*>(g), *reinterpret_cast<const uint32_t*>(&r));
+            } else if constexpr (NW == 2) {
+              const uint2 t = *reinterpret_cast<const uint2*>(q);
+              const __nv_bfloat162 r0 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.x), k2[0]);
+              const __nv_bfloat162 r1 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.y), k2[1]);
+              if (inb)
+                __stcs(reinterpret_cast<uint2*>(g), make_uint2(*reinterpret_cast<const uint32_t*>(&r0),
+                                                               *reinterpret_cast<const uint32_t*>(&r1)));
+            } else {
+              const uint4 t = *reinterpret_cast<const uint4*>(q);
+              const __nv_bfloat162 r0 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.x), k2[0]);
+              const __nv_bfloat162 r1 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.y), k2[1]);
+              const __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.z), k2[2]);
+              const __nv_bfloat162 r3 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&t.w), k2[3]);
+              if (inb)
+                __stcs(reinterpret_cast<uint4*>(g),
+                       make_uint4(*reinterpret_cast<const uint32_t*>(&r0), *reinterpret_cast<const uint32_t*>(&r1),
+                                  *reinterpret_cast<const uint32_t*>(&r2), *reinterpret_cast<const uint32_t*>(&r3)));
+            }
+          };
+#pragma unroll 8
+          for (c = c_lo; c < c_hi; ++c, gp += hw) mul_store(col + c * ROW, gp);
+          T* gy = reinterpret_cast<T*>(p.dlogits) + (int64_t)b * C * p.HW + px;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (sub[j] != 0.f && ys[j] >= c_lo && ys[j] < c_hi)
+              V::st1(gy + (int64_t)ys[j] * p.HW + j, fmaf(ey[j], kfac[j], -sub[j]));
+        }
       } else {
         c = c_lo;
 #pragma unroll 1
         for (; c + UNR <= c_hi; c += UNR) {
           float v[UNR][VEC];
 #pragma unroll
-          for (int u = 0; u < UNR; ++u) ldsv(col + (c + u) * ROW, v[u]);
+          for (int u = 0; u < UNR; ++u) ldrow(c + u, u, v[u]);
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
             float g[VEC];
@@ -523,10 +701,25 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
             gp += hw;
           }
         }
+        if (c + 4 <= c_hi) {
+          float v[4][VEC];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ldrow(c + u, u, v[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float g[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+              g[j] = ex2_approx(fmaf(v[u][j], kLog2e, -mL[j])) * kfac[j];
+            stgv(gp, g);
+            gp += hw;
+          }
+          c += 4;
+        }
 #pragma unroll 1
         for (; c < c_hi; ++c, gp += hw) {
           float v[VEC], g[VEC];
-          ldsv(col + c * ROW, v);
+          ldrow(c, -1, v);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) g[j] = ex2_approx(fmaf(v[j], kLog2e, -mL[j])) * kfac[j];
           stgv(gp, g);
@@ -542,6 +735,11 @@ __device__ __forceinline__ void process_tile(const LossParams& p, const T* __res
   }
 
   if (half == 0) {
+    if (cls != nullptr) {  // warp-uniform: the caller counts (now or one tile later)
+      cls->b = b;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) cls->t[j] = valid[j] ? y[j] : -1, cls->q[j] = amx[j];
+    }
     if (p.pred != nullptr && inb) {
       if constexpr (STR) {
 #pragma unroll
@@ -621,18 +819,32 @@ __global__ void __launch_bounds__(G == 2 ? 1024 : 512, 1)
     int k = 0;
     uint32_t round = 0;
     const bool has_partial = (p.HW % ROW) != 0;
+    const bool counting = p.counts != nullptr && half == 0;
+    TileCls<VEC> prev, now;
+    bool pending = false;
     for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles; tile += W * gridDim.x) {
       const int s = w * K + k;
+      const bool partial = has_partial && (tile % p.tiles_per_img) == p.tiles_per_img - 1;
+      int y[VEC];  // label loads in flight while the stage arrives
+      if (partial) tile_labels<VEC, true, false>(p, tile, lane, y);
+      else tile_labels<VEC, false, false>(p, tile, lane, y);
+      if (pending) count_tile<VEC>(p, prev);  // the previous tile's class counters (see TileCls)
       mbar_wait(full + s, round & 1u);
-      const T* st = reinterpret_cast<const T*>(smem + (size_t)s * stage_bytes);
-      if (has_partial && (tile % p.tiles_per_img) == p.tiles_per_img - 1)
-        process_tile<T, VEC, G, true>(p, st, tile, lane, half, xch);
+      T* st = reinterpret_cast<T*>(smem + (size_t)s * stage_bytes);
+      TileCls<VEC>* out = counting ? &now : nullptr;
+      if (partial)
+        process_tile<T, VEC, G, true>(p, st, tile, lane, half, xch, y, out);
       else
-        process_tile<T, VEC, G, false>(p, st, tile, lane, half, xch);
+        process_tile<T, VEC, G, false>(p, st, tile, lane, half, xch, y, out);
+      if (counting) prev = now;
+      pending = counting;
+      if constexpr (sizeof(T) == 2)  // bf16 writes e into the stage: order those generic-proxy stores before the
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // TMA (async proxy) refill of the same bytes
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++k == K) k = 0, ++round;
     }
+    if (pending) count_tile<VEC>(p, prev);
   }
 }
 
@@ -694,10 +906,17 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
     }
     __syncwarp();
     const int tin = tile % p.tiles_per_img;
-    if ((int64_t)(tin + 1) * 32 <= p.HW)
-      process_tile<float, 1, 1, false>(p, cur, tile, lane, 0, PairXch{});
-    else
-      process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{});
+    int y[1];
+    TileCls<1> cls;
+    TileCls<1>* out = p.counts != nullptr ? &cls : nullptr;
+    if ((int64_t)(tin + 1) * 32 <= p.HW) {
+      tile_labels<1, false, false>(p, tile, lane, y);
+      process_tile<float, 1, 1, false>(p, cur, tile, lane, 0, PairXch{}, y, out);
+    } else {
+      tile_labels<1, true, false>(p, tile, lane, y);
+      process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
+    }
+    if (out != nullptr) count_tile<1>(p, cls);
     __syncwarp();
   }
 }
@@ -758,10 +977,109 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
     }
     __syncwarp();
     const int tin = tile % p.tiles_per_img;
-    if ((int64_t)(tin + 1) * ROW <= p.HW)
-      process_tile<float, VEC, 1, false, true>(p, cur, tile, lane, 0, PairXch{});
-    else
-      process_tile<float, VEC, 1, true, true>(p, cur, tile, lane, 0, PairXch{});
+    int y[VEC];
+    TileCls<VEC> cls;
+    TileCls<VEC>* out = p.counts != nullptr ? &cls : nullptr;
+    if ((int64_t)(tin + 1) * ROW <= p.HW) {
+      tile_labels<VEC, false, true>(p, tile, lane, y);
+      process_tile<float, VEC, 1, false, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
+    } else {
+      tile_labels<VEC, true, true>(p, tile, lane, y);
+      process_tile<float, VEC, 1, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
+    }
+    if (out != nullptr) count_tile<VEC>(p, cls);
+    __syncwarp();
+  }
+}
+
+// The same case with 16-byte copies (one 4-byte cp.async per logit kept the copy pipe busy
+// ~70 % of the time at the roofline rate -- LDGSTS costs ~8 cycles per warp instruction whatever its width).
+// A channel row of a tile starts at an arbitrary 4-byte phase of global memory (row stride HW*4 bytes is not a
+// multiple of 16), but the ALIGNED chunks that cover it can be copied 16 bytes at a time: ROW/4 + 1 chunks per row
+// into a stage row of ROW + 4 floats, a flat (row, chunk) item list strided over the lanes so every copy
+// instruction is full.  The consumer side (process_tile<..., STR, OVF>) reads pixel i of row c at column
+// phase(c) + i.  Chunks beyond the tensor are zero-filled (src-size < 16); up to 3 floats of over-fetch per row
+// come from the neighbouring rows' bytes of the same tensor, i.e. from L2.
+template <int VEC>
+__global__ void __launch_bounds__(256) loss_generic_ovf_kernel(const LossParams p, const int K, const int64_t n_total) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int ROW = 32 * VEC, RS = ROW + 4, NCH = ROW / 4 + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int stage_elems = p.C * RS;
+  float* bufs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * K * stage_elems;
+  const float* logits = reinterpret_cast<const float*>(p.logits);
+  const int n_items = p.C * NCH;
+  auto row0 = [&](int tile) {  // element offset of the tile's first pixel in channel 0 of its image
+    const int b = tile / p.tiles_per_img;
+    return (int64_t)b * p.C * p.HW + (int64_t)(tile - b * p.tiles_per_img) * ROW;
+  };
+  // Offsets inside an image fit 32 bits (the launcher checks C*HW < 2^31 - ROW): per item the address is
+  // the tile's aligned base pointer + 4 * (((r0 + c*HW) & ~3) + 4k) with r0 = (image base + first pixel) & 3
+  // carried into the 32-bit part; only a tile that can reach the end of the tensor takes the bounds-checked
+  // copy size.
+  auto issue = [&](int tile, float* dst) {
+    const int b = tile / p.tiles_per_img;
+    const int p0 = (tile - b * p.tiles_per_img) * ROW;
+    const int64_t img = (int64_t)b * p.C * p.HW;
+    const float* base = logits + (img & ~(int64_t)3);  // 16-byte aligned
+    const int r0 = (int)(img & 3) + p0;
+    const int hw = (int)p.HW;
+    const uint32_t d0 = smem_u32(dst);
+    const bool near_end = (img & ~(int64_t)3) + r0 + (int64_t)(p.C - 1) * hw + ROW + 8 > n_total;
+    if (!near_end) {
+#pragma unroll 4
+      for (int i = lane; i < n_items; i += 32) {
+        const int c = i / NCH, k = i - c * NCH;
+        const int off = ((r0 + c * hw) & ~3) + 4 * k;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 4u * (uint32_t)(c * RS + 4 * k)),
+                     "l"(base + off)
+                     : "memory");
+      }
+    } else {
+      const int64_t left0 = n_total - (img & ~(int64_t)3);  // elements from `base` to the end of the tensor
+      for (int i = lane; i < n_items; i += 32) {
+        const int c = i / NCH, k = i - c * NCH;
+        const int off = ((r0 + c * hw) & ~3) + 4 * k;
+        const int64_t rem = left0 - off;
+        const int nbytes = rem >= 4 ? 16 : (rem > 0 ? 4 * (int)rem : 0);  // src-size < 16: zero-fill the rest
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + 4u * (uint32_t)(c * RS + 4 * k)),
+                     "l"(base + (rem > 0 ? off : 0)), "r"(nbytes)
+                     : "memory");
+      }
+    }
+    cp_async_commit();
+  };
+  const int stride = gridDim.x * W;
+  int tile = blockIdx.x * W + warp;
+  int k = 0;
+  if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
+  for (; tile < p.num_tiles; tile += stride) {
+    float* cur = bufs + (size_t)k * stage_elems;
+    const int tin = tile % p.tiles_per_img;
+    const bool full = (int64_t)(tin + 1) * ROW <= p.HW;
+    int y[VEC];  // label loads in flight while the copies land
+    if (full) tile_labels<VEC, false, true>(p, tile, lane, y);
+    else tile_labels<VEC, true, true>(p, tile, lane, y);
+    if (K == 2) {
+      const int next = tile + stride;
+      if (next < p.num_tiles) {
+        issue(next, bufs + (size_t)(k ^ 1) * stage_elems);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      k ^= 1;
+    } else {
+      issue(tile, cur);
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const int ph0 = (int)(row0(tile) & 3);
+    TileCls<VEC> cls;
+    TileCls<VEC>* out = p.counts != nullptr ? &cls : nullptr;
+    if (full) process_tile<float, VEC, 1, false, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
+    else process_tile<float, VEC, 1, true, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
+    if (out != nullptr) count_tile<VEC>(p, cls);
     __syncwarp();
   }
 }
@@ -781,7 +1099,12 @@ __global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
     for (int c = 0; c < p.C; ++c)
       stage[c * 32 + lane] = inb ? src[(int64_t)c * p.HW] : T(0.f);
     __syncwarp();
-    process_tile<T, 1, 1, true>(p, stage, tile, lane, 0, PairXch{});
+    int y[1];
+    tile_labels<1, true, false>(p, tile, lane, y);
+    TileCls<1> cls;
+    TileCls<1>* out = p.counts != nullptr ? &cls : nullptr;
+    process_tile<T, 1, 1, true>(p, stage, tile, lane, 0, PairXch{}, y, out);
+    if (out != nullptr) count_tile<1>(p, cls);
     __syncwarp();
   }
 }
@@ -928,6 +1251,37 @@ static int launch_generic(const LossParams& p0, cudaStream_t stream, int* tiles_
   const size_t stage = (size_t)p.C * 32 * sizeof(T);
   ROBSEG_REQUIRE(stage <= kSmemBudget, "C=%d too large for one shared-memory stage", p.C);
   if constexpr (sizeof(T) == 4) {
+    // 16-byte over-fetch path (default when the logits pointer is 16-byte aligned; ROBSEG_LOSS_GENERIC_OVF=0
+    // restores the 4-byte-copy kernels below): 2 pixels per lane while >= 16 warps per SM keep two stages each,
+    // else 1 pixel per lane with as many warps as fit (two stages when >= 16 of them do).
+    const char* ovf_env = getenv("ROBSEG_LOSS_GENERIC_OVF");
+    if (reinterpret_cast<uintptr_t>(p.logits) % 16 == 0 && !(ovf_env && atoi(ovf_env) == 0)) {
+      auto st_bytes = [&](int v) { return (size_t)p.C * (32 * v + 4) * sizeof(float); };
+      int vec = (size_t)16 * 2 * st_bytes(2) <= kSmemBudget ? 2 : 1;
+      if (ovf_env && (atoi(ovf_env) == 1 || atoi(ovf_env) == 2 || atoi(ovf_env) == 4)) vec = atoi(ovf_env);
+      const size_t st = st_bytes(vec);
+      // at least 4 warps with one stage each and 32-bit offsets inside an image, else the old kernels
+      if (st * 4 <= kSmemBudget && (int64_t)p.C * p.HW < ((int64_t)1 << 31) - 1024) {
+        int K = (size_t)16 * 2 * st <= kSmemBudget ? 2 : 1;
+        if (vec == 4 && (size_t)8 * 2 * st <= kSmemBudget) K = 2;
+        int warps_sm = (int)(kSmemBudget / (K * st));
+        if (warps_sm > 32) warps_sm = 32;
+        const int W = warps_sm >= 8 ? 8 : warps_sm;
+        const int ctas_sm = warps_sm / W;
+        const size_t smem = (size_t)W * K * st;
+        auto kern = vec == 4 ? loss_generic_ovf_kernel<4> : vec == 2 ? loss_generic_ovf_kernel<2> : loss_generic_ovf_kernel<1>;
+        ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        p.tiles_per_img = *tiles_per_img = (int)((p.HW + 32 * vec - 1) / (32 * vec));
+        p.num_tiles = p.B * p.tiles_per_img;
+        int grid = sm_count() * ctas_sm;
+        const int max_useful = (p.num_tiles + W - 1) / W;
+        if (grid > max_useful) grid = max_useful;
+        if (grid < 1) grid = 1;
+        kern<<<grid, 32 * W, smem, stream>>>(p, K, (int64_t)p.B * p.C * p.HW);
+        ROBSEG_LAUNCH_CHECK();
+        return 0;
+      }
+    }
     // wide strided tiles while >= 16 warps per SM keep two stages each (C <= 13 at 4 pixels per
     // lane, <= 27 at 2; measured at 24x21x473x473: 0.27 ms at 2, 0.29-0.35 ms at 4 with 10 warps,
     // 0.33 ms at 1); otherwise one pixel per lane.  ROBSEG_LOSS_GENERIC_VEC forces a width that
@@ -1010,13 +1364,13 @@ extern "C" size_t robseg_loss_workspace_bytes(int B, int C, int64_t HW, int dtyp
   return (size_t)tiles_upper_bound(B, HW) * sizeof(float4);
 }
 
-extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t* labels,
-                                   const float* class_w, int loss_kind, int ignore_index, int B,
-                                   int C, int64_t HW, const float* grad_scale,
-                                   const float* upstream_pix, void* dlogits, float* loss_pix,
-                                   int64_t* pred, float* loss_img, float* track_img,
-                                   int32_t* correct_img, int32_t* valid_img, void* workspace,
-                                   size_t workspace_bytes, robseg_stream_t stream_) {
+static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* labels,
+                             const float* class_w, int loss_kind, int ignore_index, int B,
+                             int C, int64_t HW, const float* grad_scale,
+                             const float* upstream_pix, void* dlogits, float* loss_pix,
+                             int64_t* pred, float* loss_img, float* track_img,
+                             int32_t* correct_img, int32_t* valid_img, int64_t* counts, void* workspace,
+                             size_t workspace_bytes, robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ROBSEG_REQUIRE(logits && labels, "logits/labels must not be NULL");
   ROBSEG_REQUIRE(dtype == ROBSEG_F32 || dtype == ROBSEG_BF16, "unsupported dtype %d", dtype);
@@ -1034,6 +1388,9 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
   p.partials = static_cast<float4*>(workspace);
   p.HW = HW, p.kind = loss_kind, p.ignore_index = ignore_index, p.B = B, p.C = C;
   p.inv_hw = (float)(1.0 / (double)HW);
+  p.counts = reinterpret_cast<unsigned long long*>(counts);
+  if (counts != nullptr)
+    ROBSEG_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * C * sizeof(int64_t), stream));
 
   const int esize = dtype == ROBSEG_F32 ? 4 : 2;
   auto al16 = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
@@ -1067,4 +1424,29 @@ extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t*
     ROBSEG_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int robseg_loss_fwd_bwd(const void* logits, int dtype, const int64_t* labels,
+                                   const float* class_w, int loss_kind, int ignore_index, int B,
+                                   int C, int64_t HW, const float* grad_scale,
+                                   const float* upstream_pix, void* dlogits, float* loss_pix,
+                                   int64_t* pred, float* loss_img, float* track_img,
+                                   int32_t* correct_img, int32_t* valid_img, void* workspace,
+                                   size_t workspace_bytes, robseg_stream_t stream) {
+  return loss_fwd_bwd_impl(logits, dtype, labels, class_w, loss_kind, ignore_index, B, C, HW, grad_scale,
+                           upstream_pix, dlogits, loss_pix, pred, loss_img, track_img, correct_img, valid_img,
+                           nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int robseg_loss_fwd_bwd_counts(const void* logits, int dtype, const int64_t* labels,
+                                          const float* class_w, int loss_kind, int ignore_index, int B,
+                                          int C, int64_t HW, const float* grad_scale,
+                                          const float* upstream_pix, void* dlogits, float* loss_pix,
+                                          int64_t* pred, float* loss_img, float* track_img,
+                                          int32_t* correct_img, int32_t* valid_img, int64_t* counts,
+                                          void* workspace, size_t workspace_bytes, robseg_stream_t stream) {
+  ROBSEG_REQUIRE(counts != nullptr, "counts must not be NULL");
+  return loss_fwd_bwd_impl(logits, dtype, labels, class_w, loss_kind, ignore_index, B, C, HW, grad_scale,
+                           upstream_pix, dlogits, loss_pix, pred, loss_img, track_img, correct_img, valid_img,
+                           counts, workspace, workspace_bytes, stream);
 }

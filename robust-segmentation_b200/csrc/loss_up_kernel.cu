@@ -41,6 +41,7 @@ struct LossUpParams {
   float4* contrib;  // [B][h+1][C][w+1] corner contributions (a,b,c,d), or nullptr (no gradient)
   int64_t* pred;
   float4* partials;
+  unsigned long long* counts;  // [B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
   int kind, ignore_index, B, C, h, w, H, W;
   int groups_x, tiles_per_img, num_tiles;
   float inv_hw;
@@ -329,6 +330,12 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
       }
     }
 
+    if (p.counts != nullptr) {  // warp-uniform; pixels outside the image carry y = ignore_index
+      unsigned long long* cnt = p.counts + (size_t)b * 3 * C;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        count_pixel(cnt, C, (y[r] != p.ignore_index) && (y[r] >= 0) && (y[r] < C), y[r], amx[r]);
+    }
     if (p.pred != nullptr && lane_ok) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -418,12 +425,12 @@ extern "C" size_t robseg_loss_upsampled_workspace_bytes(int B, int C, int h, int
   return partial_bytes(B, h, W, R) + contrib_bytes(B, C, h, w);
 }
 
-extern "C" int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* labels, const float* class_w,
-                                             int loss_kind, int ignore_index, int B, int C, int h, int w,
-                                             int H, int W, const float* grad_scale, float* dlow,
-                                             int64_t* pred, float* loss_img, float* track_img,
-                                             int32_t* correct_img, int32_t* valid_img, void* workspace,
-                                             size_t workspace_bytes, robseg_stream_t stream_) {
+static int loss_upsampled_impl(const float* low, const int64_t* labels, const float* class_w,
+                               int loss_kind, int ignore_index, int B, int C, int h, int w,
+                               int H, int W, const float* grad_scale, float* dlow,
+                               int64_t* pred, float* loss_img, float* track_img,
+                               int32_t* correct_img, int32_t* valid_img, int64_t* counts, void* workspace,
+                               size_t workspace_bytes, robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ROBSEG_REQUIRE(low && labels, "low/labels must not be NULL");
   ROBSEG_REQUIRE(loss_kind >= ROBSEG_LOSS_CE && loss_kind <= ROBSEG_LOSS_ARGMAX, "unknown loss kind %d", loss_kind);
@@ -444,6 +451,9 @@ extern "C" int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* la
                         : nullptr;
   p.kind = loss_kind, p.ignore_index = ignore_index, p.B = B, p.C = C, p.h = h, p.w = w, p.H = H, p.W = W;
   p.inv_hw = (float)(1.0 / ((double)H * W));
+  p.counts = reinterpret_cast<unsigned long long*>(counts);
+  if (counts != nullptr)
+    ROBSEG_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * C * sizeof(int64_t), stream));
   int rc = R == 16 ? launch_up<16>(p, stream) : R == 8 ? launch_up<8>(p, stream)
            : R == 4 ? launch_up<4>(p, stream) : launch_up<2>(p, stream);
   if (rc != 0) return rc;
@@ -461,4 +471,28 @@ extern "C" int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* la
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+extern "C" int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* labels, const float* class_w,
+                                             int loss_kind, int ignore_index, int B, int C, int h, int w,
+                                             int H, int W, const float* grad_scale, float* dlow,
+                                             int64_t* pred, float* loss_img, float* track_img,
+                                             int32_t* correct_img, int32_t* valid_img, void* workspace,
+                                             size_t workspace_bytes, robseg_stream_t stream) {
+  return loss_upsampled_impl(low, labels, class_w, loss_kind, ignore_index, B, C, h, w, H, W, grad_scale, dlow,
+                             pred, loss_img, track_img, correct_img, valid_img, nullptr, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int robseg_loss_upsampled_fwd_bwd_counts(const float* low, const int64_t* labels,
+                                                    const float* class_w, int loss_kind, int ignore_index,
+                                                    int B, int C, int h, int w, int H, int W,
+                                                    const float* grad_scale, float* dlow, int64_t* pred,
+                                                    float* loss_img, float* track_img, int32_t* correct_img,
+                                                    int32_t* valid_img, int64_t* counts, void* workspace,
+                                                    size_t workspace_bytes, robseg_stream_t stream) {
+  ROBSEG_REQUIRE(counts != nullptr, "counts must not be NULL");
+  return loss_upsampled_impl(low, labels, class_w, loss_kind, ignore_index, B, C, h, w, H, W, grad_scale, dlow,
+                             pred, loss_img, track_img, correct_img, valid_img, counts, workspace,
+                             workspace_bytes, stream);
 }

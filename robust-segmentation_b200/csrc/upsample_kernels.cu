@@ -13,6 +13,8 @@
 // i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace robseg {
 
 struct Tap {
@@ -263,6 +265,119 @@ __global__ void __launch_bounds__(128)
         v[j] = ky.k[i][0] * hx[0][j] + ky.k[i][1] * hx[1][j] + ky.k[i][2] * hx[2][j];
       store_row<R>(o + (int64_t)i * W, v);
     }
+  }
+}
+
+// x2 with even h, w (the decode head's top-down path, uperforseg.py:282-303): one input cell per thread
+// gives 16 bytes of output per 9 loads and ran at 53 % of the roofline, latency-bound (few bytes in flight
+// per warp).  Here a thread owns a 2x2 block of input cells -> a 4x4 output block: 4 rows x (scalar +
+// 8-byte + scalar) loads, 4 rows x one 16-byte store (a warp writes 512 contiguous bytes per row), and
+// the next plane's 12 loads are issued before the current plane is reduced.  Every output has exactly two
+// taps per axis at compile-time positions of the 4x4 neighbourhood (rows / columns a0-1 .. a0+2, clamped
+// at the borders, where make_tap's weights (1, 0) / (w0, w1) reproduce ATen's clamped expression).
+struct X2In {
+  float v[4][4];
+};
+__device__ __forceinline__ void x2_load(X2In& q, const float* __restrict__ base, const int (&row)[4], int w,
+                                        int cm, int b0, int cp) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float* rp = base + (int64_t)row[r] * w;
+    const float2 mid = __ldg(reinterpret_cast<const float2*>(rp + b0));
+    q.v[r][0] = __ldg(rp + cm), q.v[r][1] = mid.x, q.v[r][2] = mid.y, q.v[r][3] = __ldg(rp + cp);
+  }
+}
+
+__global__ void __launch_bounds__(128, 7)
+    upsample_fwd_x2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h,
+                           int w) {
+  const int hw2 = w >> 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (h >> 1) * hw2) return;
+  const int a0 = 2 * (t / hw2), b0 = 2 * (t % hw2);
+  const int H = 2 * h, W = 2 * w;
+  // output j (0..3) along an axis: cell j/2, sub-position j%2; taps at neighbourhood slots
+  // (j/2 + j%2, j/2 + j%2 + 1).  For x2 ATen's weights (make_tap) are the constants (w0, w1) = (.25, .75) for
+  // even and (.75, .25) for odd outputs -- exactly, src = 0.5*(dst+0.5)-0.5 has no rounding -- except output 0
+  // of the image, whose clamped source coordinate gives (1, 0): one run-time weight per axis.
+  const float lx1 = b0 == 0 ? 0.f : 0.75f, lx0 = 1.f - lx1;
+  const float ly1 = a0 == 0 ? 0.f : 0.75f, ly0 = 1.f - ly1;
+  const float wx0[4] = {lx0, 0.75f, 0.25f, 0.75f}, wx1[4] = {lx1, 0.25f, 0.75f, 0.25f};
+  const float wy0[4] = {ly0, 0.75f, 0.25f, 0.75f}, wy1[4] = {ly1, 0.25f, 0.75f, 0.25f};
+  const int cm = max(b0 - 1, 0), cp = min(b0 + 2, w - 1);
+  const int row[4] = {max(a0 - 1, 0), a0, a0 + 1, min(a0 + 2, h - 1)};
+  int64_t p = blockIdx.z;
+  if (p >= planes) return;
+  X2In cur, nxt;
+  x2_load(cur, in + p * (int64_t)h * w, row, w, cm, b0, cp);
+  for (; p < planes; p += gridDim.z) {
+    const int64_t pn = p + gridDim.z;
+    if (pn < planes) x2_load(nxt, in + pn * (int64_t)h * w, row, w, cm, b0, cp);
+    float hx[4][4];  // [neighbourhood row][output column]
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = (j >> 1) + (j & 1);
+        hx[r][j] = wx0[j] * cur.v[r][s] + wx1[j] * cur.v[r][s + 1];
+      }
+    float* o = out + (p * H + 2 * a0) * (int64_t)W + 2 * b0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = (i >> 1) + (i & 1);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = wy0[i] * hx[s][j] + wy1[i] * hx[s + 1][j];
+      __stcs(reinterpret_cast<float4*>(o + (int64_t)i * W), make_float4(v[0], v[1], v[2], v[3]));
+    }
+    cur = nxt;
+  }
+}
+
+// x2 backward with even h, w: the mirror image of upsample_fwd_x2_kernel.  A thread owns a 2x2 block of input
+// cells and gathers their gradient from the 6x6 output block that touches them: 6 rows x (scalar + 16-byte +
+// scalar) loads -- the vector loads of a warp are contiguous, the two scalars are its neighbours' words -- then
+// two 8-byte stores.  Flat thread -> cell mapping (16- and 32-wide pyramid planes fill their warps, which the
+// walk-down kernel's one-lane-per-column layout does not: 18 of 32 lanes at w = 16), 18 independent loads in
+// flight per thread, every input cell written once, no atomics, fixed summation order (bit-reproducible).
+// Weights: an interior cell receives (.25, .75, .75, .25) from output rows 2a-1 .. 2a+2 (ATen's taps for x2,
+// exact in fp32); at the image border the missing outer row weighs 0 and the clamped one 1 instead of .75.
+__global__ void __launch_bounds__(128, 6)
+    upsample_bwd_x2_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes, int C,
+                           int64_t bs, int64_t cs, int h, int w) {
+  const int hw2 = w >> 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (h >> 1) * hw2) return;
+  const int a0 = 2 * (t / hw2), b0 = 2 * (t % hw2);
+  const int H = 2 * h, W = 2 * w;
+  // run-time weights of the four border-sensitive taps per axis
+  const float xa0 = b0 == 0 ? 0.f : 0.25f, xa1 = b0 == 0 ? 1.f : 0.75f;
+  const float xb2 = b0 + 2 == w ? 1.f : 0.75f, xb3 = b0 + 2 == w ? 0.f : 0.25f;
+  const float ya0 = a0 == 0 ? 0.f : 0.25f, ya1 = a0 == 0 ? 1.f : 0.75f;
+  const float yb2 = a0 + 2 == h ? 1.f : 0.75f, yb3 = a0 + 2 == h ? 0.f : 0.25f;
+  const int X0 = 2 * b0;                                    // first of my four aligned output columns
+  const int xl = max(X0 - 1, 0), xr = min(X0 + 4, W - 1);   // clamped neighbours (weight 0 when clamped)
+  int row[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) row[r] = min(max(2 * a0 - 1 + r, 0), H - 1);
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* base = gout + (p / C) * bs + (p % C) * cs;
+    float c0[6], c1[6];  // x-reduced rows for my two cell columns
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const float* rp = base + (int64_t)row[r] * W;
+      const float4 m = __ldcs(reinterpret_cast<const float4*>(rp + X0));
+      const float l = __ldg(rp + xl), q = __ldg(rp + xr);
+      c0[r] = ((xa0 * l + xa1 * m.x) + 0.75f * m.y) + 0.25f * m.z;
+      c1[r] = ((0.25f * m.y + 0.75f * m.z) + xb2 * m.w) + xb3 * q;
+    }
+    float* o = gin + (p * h + a0) * (int64_t)w + b0;
+    __stcs(reinterpret_cast<float2*>(o),
+           make_float2(((ya0 * c0[0] + ya1 * c0[1]) + 0.75f * c0[2]) + 0.25f * c0[3],
+                       ((ya0 * c1[0] + ya1 * c1[1]) + 0.75f * c1[2]) + 0.25f * c1[3]));
+    __stcs(reinterpret_cast<float2*>(o + w),
+           make_float2(((0.25f * c0[2] + 0.75f * c0[3]) + yb2 * c0[4]) + yb3 * c0[5],
+                       ((0.25f * c1[2] + 0.75f * c1[3]) + yb2 * c1[4]) + yb3 * c1[5]));
   }
 }
 
@@ -521,6 +636,30 @@ static int launch_fwd_pow2(const float* in, float* out, int64_t planes, int h, i
   return 0;
 }
 
+static int launch_fwd_x2(const float* in, float* out, int64_t planes, int h, int w, cudaStream_t stream) {
+  const int cells = (h >> 1) * (w >> 1);
+  const int gx = (cells + 127) / 128;
+  // 72 registers -> 7 resident blocks per SM: two full waves of blocks, the rest of the planes in the block's loop
+  int64_t gz = ((int64_t)sm_count() * 14 + gx - 1) / gx;
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  upsample_fwd_x2_kernel<<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(in, out, planes, h, w);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_bwd_x2(const float* gout, float* gin, int64_t planes, int C, int64_t bs, int64_t cs, int h,
+                         int w, cudaStream_t stream) {
+  const int cells = (h >> 1) * (w >> 1);
+  const int gx = (cells + 127) / 128;
+  int64_t gz = ((int64_t)sm_count() * 12 + gx - 1) / gx;  // two waves of 6 resident blocks per SM
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  upsample_bwd_x2_kernel<<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(gout, gin, planes, C, bs, cs, h, w);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int R>
 static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C, int64_t bs, int64_t cs,
                            int h, int w, cudaStream_t stream) {
@@ -551,7 +690,10 @@ extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int
   if (H % h == 0 && W % w == 0 && H / h == W / w && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
       (int64_t)h * w < ((int64_t)1 << 30)) {
     switch (H / h) {
-      case 2: return launch_fwd_pow2<2>(in, out, planes, h, w, stream);
+      case 2:
+        if (h % 2 == 0 && w % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 8 == 0 && !getenv("ROBSEG_UP_X2_CELL"))
+          return launch_fwd_x2(in, out, planes, h, w, stream);
+        return launch_fwd_pow2<2>(in, out, planes, h, w, stream);
       case 4: return launch_fwd_pow2<4>(in, out, planes, h, w, stream);
       case 8: return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
       default: break;
@@ -584,7 +726,10 @@ extern "C" int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N
   if (H % h == 0 && W % w == 0 && H / h == W / w && reinterpret_cast<uintptr_t>(gout) % 16 == 0 &&
       bs % 4 == 0 && cs % 4 == 0) {
     switch (H / h) {
-      case 2: return launch_bwd_pow2<2>(gout, gin, planes, C, bs, cs, h, w, stream);
+      case 2:
+        if (h % 2 == 0 && w % 2 == 0 && reinterpret_cast<uintptr_t>(gin) % 8 == 0 && !getenv("ROBSEG_UP_X2_CELL"))
+          return launch_bwd_x2(gout, gin, planes, C, bs, cs, h, w, stream);
+        return launch_bwd_pow2<2>(gout, gin, planes, C, bs, cs, h, w, stream);
       case 4: return launch_bwd_pow2<4>(gout, gin, planes, C, bs, cs, h, w, stream);
       case 8: return launch_bwd_pow2<8>(gout, gin, planes, C, bs, cs, h, w, stream);
       case 16: return launch_bwd_pow2<16>(gout, gin, planes, C, bs, cs, h, w, stream);

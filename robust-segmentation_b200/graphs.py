@@ -121,6 +121,7 @@ class GraphedAttack:
         self.ctl = ops.make_ctl(self.n_iter_max, dev)
         self.done_host = torch.zeros([1], dtype=torch.int32).pin_memory()
         self.pred_best = torch.zeros_like(self.y) if keep_pred else None
+        self.counts_best = None  # [B,3,C] int64, allocated with the first capture (C is known then)
         self.weights = None  # [C] class weights, allocated on first use
         self.pool = None
         self.graphs = {}     # loss kind -> dict(init=, it=, last=, out0=)
@@ -142,7 +143,9 @@ class GraphedAttack:
             logits = logits.float()
         w = self.weights if kind == "mask-ce-bal" else None
         fn = ops.loss_upsampled_fwd_bwd if fused else ops.loss_fwd_bwd
-        out = fn(logits, self.y, kind, w, want_grad=with_grad, want_pred=self.keep_pred)
+        out = fn(logits, self.y, kind, w, want_grad=with_grad, want_pred=self.keep_pred, want_counts=True)
+        if self.counts_best is None:
+            self.counts_best = torch.zeros_like(out.counts)
         if with_grad:
             (gx,) = torch.autograd.grad(logits, [self.x_adv], grad_outputs=out.dlogits)
             self.grad.copy_(gx)
@@ -151,8 +154,10 @@ class GraphedAttack:
             ops.apgd_bookkeep_ctl(out.correct, out.valid, track, self.acc, self.loss_best, self.loss_best_last,
                                   self.reduced_last, self.step, self.loss_steps, self.ctl, self.n_pxl,
                                   self.early_stop, self.flags, self.done)
+            jobs = [(self.counts_best, out.counts, self.flags[0], None)]
             if self.keep_pred:
-                ops.row_select([(self.pred_best, out.pred, self.flags[0], None)], self.B, self.x.device)
+                jobs.append((self.pred_best, out.pred, self.flags[0], None))
+            ops.row_select(jobs, self.B, self.x.device)
         return out, track
 
     def _capture(self, kind, track_loss):
@@ -188,7 +193,7 @@ class GraphedAttack:
 
     def run_stage(self, x, y, x_adv0, eps, n_iter, kind, track_loss, weights, checks):
         """One ``apgd_train`` call (a stage of apgd_largereps) from the starting point ``x_adv0``.
-        Returns fresh tensors ``(x_best, acc, loss_best, x_best_adv, pred_best)``."""
+        Returns fresh tensors ``(x_best, acc, loss_best, x_best_adv, pred_best, counts_best)``."""
         from . import ops
 
         if n_iter > self.n_iter_max:
@@ -221,6 +226,7 @@ class GraphedAttack:
             self.grad_best.copy_(self.grad)
             if self.keep_pred:
                 self.pred_best.copy_(out0.pred)
+            self.counts_best.copy_(out0.counts)
             copied = None
             for i in range(n_iter):
                 g["it" if i < n_iter - 1 else "last"].replay()
@@ -237,4 +243,4 @@ class GraphedAttack:
                 ops.row_select([(self.x_best_adv, xa, self.flags[0], None), (self.x_best, xa, self.flags[1], None),
                                 (self.grad_best, self.grad, self.flags[1], None)], self.B, self.x.device)
             return (self.x_best.clone(), self.acc.clone(), self.loss_best.clone(), self.x_best_adv.clone(),
-                    self.pred_best.clone() if self.keep_pred else None)
+                    self.pred_best.clone() if self.keep_pred else None, self.counts_best.clone())

@@ -15,7 +15,7 @@ KIND_IDS = {
     "js-avg": _lib.LOSS_JS, "argmax": _lib.LOSS_ARGMAX,
 }
 
-LossOut = namedtuple("LossOut", "loss_img track_img correct valid dlogits pred loss_pix")
+LossOut = namedtuple("LossOut", "loss_img track_img correct valid dlogits pred loss_pix counts", defaults=(None,))
 
 _workspaces = {}
 
@@ -79,11 +79,13 @@ def _workspace(dev, nbytes):
 
 def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=None,
                  want_grad=True, want_pred=False, want_loss_pix=False, ignore_index=-1,
-                 dlogits_out=None, want_stats=True):
+                 dlogits_out=None, want_stats=True, want_counts=False):
     """Fused softmax + loss + dlogits + argmax + per-image sums (robseg_loss_fwd_bwd).
 
     logits [B,C,*spatial] fp32/bf16 (contiguous), labels [B,*spatial] int64.
     grad_scale: None (1/HW per image), python float, or [B] tensor.
+    want_counts: also return ``counts`` [B,3,C] int64 -- the per-image intersection / target /
+    prediction class counters of compute_iou_acc taken in the same pass (robseg_loss_fwd_bwd_counts).
     Returns LossOut; fields not requested are None.
     """
     _need_cuda(logits, labels, weights, upstream)
@@ -136,18 +138,21 @@ def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=N
     # algorithmic bytes: logits read (+ gradient write) + int64 labels
     # (+ int64 argmax)
     nbytes = B * Cn * HW * logits.element_size() * (2 if want_grad else 1) + 8 * B * HW * (2 if want_pred else 1)
-    with torch.cuda.device(dev), _timed("loss_grad" if want_grad else "loss_only", nbytes):
-        rc = lib.robseg_loss_fwd_bwd(
-            logits.data_ptr(), dt, labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn,
+    counts = torch.empty((B, 3, Cn), dtype=torch.int64, device=dev) if want_counts else None
+    head = (logits.data_ptr(), dt, labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn,
             HW, _ptr(grad_scale), _ptr(upstream), _ptr(dlogits), _ptr(loss_pix), _ptr(pred),
             _ptr(fstat[0]) if want_stats else 0, _ptr(fstat[1]) if want_stats else 0,
-            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0,
-            ws.data_ptr(), ws.numel(), _stream())
+            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0)
+    with torch.cuda.device(dev), _timed("loss_grad" if want_grad else "loss_only", nbytes):
+        if want_counts:
+            rc = lib.robseg_loss_fwd_bwd_counts(*head, counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        else:
+            rc = lib.robseg_loss_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_fwd_bwd")
     _lib.count(2 if want_stats else 1)
     if want_stats:
-        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlogits, pred, loss_pix)
-    return LossOut(None, None, None, None, dlogits, pred, loss_pix)
+        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlogits, pred, loss_pix, counts)
+    return LossOut(None, None, None, None, dlogits, pred, loss_pix, counts)
 
 
 FUSED_UP_RATIOS = (2, 4, 8, 16)
@@ -163,7 +168,7 @@ def can_fuse_upsample(low, labels):
 
 
 def loss_upsampled_fwd_bwd(low, labels, kind, weights=None, grad_scale=None, want_grad=True,
-                           want_pred=False, ignore_index=-1, dlow_out=None, want_stats=True):
+                           want_pred=False, ignore_index=-1, dlow_out=None, want_stats=True, want_counts=False):
     """``loss_fwd_bwd(F.interpolate(low, labels.shape[-2:], mode="bilinear"), ...)`` without the
     [B,C,H,W] logits: the loss kernel interpolates on the fly and returns the gradient with respect to
     ``low`` (robseg_loss_upsampled_fwd_bwd).  ``LossOut.dlogits`` is ``dlow``
@@ -206,18 +211,22 @@ def loss_upsampled_fwd_bwd(low, labels, kind, weights=None, grad_scale=None, wan
     ws = _workspace(dev, lib.robseg_loss_upsampled_workspace_bytes(B, Cn, h, w, H, W))
     # algorithmic bytes: labels (+ argmax map) + the low-resolution tensors
     nbytes = 8 * B * H * W * (2 if want_pred else 1) + low.numel() * 4 * (2 if want_grad else 1)
-    with torch.cuda.device(dev), _timed("loss_up_grad" if want_grad else "loss_up_only", nbytes):
-        rc = lib.robseg_loss_upsampled_fwd_bwd(
-            low.data_ptr(), labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn, h, w, H, W,
+    counts = torch.empty((B, 3, Cn), dtype=torch.int64, device=dev) if want_counts else None
+    head = (low.data_ptr(), labels.data_ptr(), _ptr(weights), kid, int(ignore_index), B, Cn, h, w, H, W,
             _ptr(grad_scale), _ptr(dlow), _ptr(pred),
             _ptr(fstat[0]) if want_stats else 0, _ptr(fstat[1]) if want_stats else 0,
-            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0,
-            ws.data_ptr(), ws.numel(), _stream())
+            _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0)
+    with torch.cuda.device(dev), _timed("loss_up_grad" if want_grad else "loss_up_only", nbytes):
+        if want_counts:
+            rc = lib.robseg_loss_upsampled_fwd_bwd_counts(*head, counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                          _stream())
+        else:
+            rc = lib.robseg_loss_upsampled_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_upsampled_fwd_bwd")
     _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0))
     if want_stats:
-        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlow, pred, None)
-    return LossOut(None, None, None, None, dlow, pred, None)
+        return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlow, pred, None, counts)
+    return LossOut(None, None, None, None, dlow, pred, None, counts)
 
 
 def _f32c(t, name):

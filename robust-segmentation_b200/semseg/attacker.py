@@ -18,9 +18,11 @@ The only data-dependent host decision left is ``early_stop`` (:568-569); it is r
 iteration late from a pinned flag while the device freezes the state itself, so results
 do not depend on when the host notices.
 
-Out of scope: L2 / L1 norms, DLR / margin losses, apgd_restarts,
-pgd_filters -- never reached from tools/infer.py (norm is hard-set to "Linf" at
-tools/infer.py:327).  They raise NotImplementedError here.
+Out of scope: L2 / L1 norms and pgd_filters -- never reached from
+tools/infer.py (norm is hard-set to "Linf" at tools/infer.py:327); they raise
+NotImplementedError.  ``dlr_loss`` / ``dlr_loss_targeted`` / ``margin_loss`` are kept for name
+parity as plain differentiable PyTorch expressions (no kernel: no driver selects them), and
+``apgd_restarts`` (untargeted) runs on top of the accelerated ``apgd_train``.
 """
 from functools import partial
 
@@ -30,7 +32,8 @@ from .. import ops
 
 __all__ = ["compute_iou_acc", "masked_cross_entropy", "masked_cross_entropy_balanced",
            "js_div_fn", "js_loss", "pixel_to_img_loss", "check_oscillation", "criterion_dict",
-           "apgd_train", "apgd_largereps", "apgd_restarts", "apgd_schedule"]
+           "apgd_train", "apgd_largereps", "apgd_restarts", "apgd_schedule", "dlr_loss",
+           "dlr_loss_targeted", "margin_loss"]
 
 
 class Logger:
@@ -113,6 +116,36 @@ def js_loss(p, q, num_classes=21, reduction="mean"):
         return loss
 
 
+# Name parity only (semseg/attacker.py:123-141,176-184): the three margin-type losses of the reference's
+# module.  No SEA / PIR-AT driver selects them, so they stay stock PyTorch on whatever device the logits
+# live on; written from the published definitions (Croce & Hein 2020, DLR), class axis = 1.
+def _top_logits(x, k):
+    return x.topk(k, dim=1).values  # descending along the class axis
+
+
+def dlr_loss(x, y, reduction="none"):
+    """Difference-of-logits-ratio: -(z_y - max_{k != y} z_k) / (z_(1) - z_(3) + 1e-12)."""
+    top = _top_logits(x, 3)
+    z_y = x.gather(1, y.unsqueeze(1)).squeeze(1)
+    y_is_top = (x.argmax(1) == y).to(x.dtype)
+    best_other = top[:, 1] * y_is_top + top[:, 0] * (1.0 - y_is_top)
+    return -(z_y - best_other) / (top[:, 0] - top[:, 2] + 1e-12)
+
+
+def dlr_loss_targeted(x, y, y_target):
+    """Targeted DLR: -(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12)."""
+    top = _top_logits(x, 4)
+    z_y = x.gather(1, y.unsqueeze(1)).squeeze(1)
+    z_t = x.gather(1, y_target.unsqueeze(1)).squeeze(1)
+    return -(z_y - z_t) / (top[:, 0] - 0.5 * (top[:, 2] + top[:, 3]) + 1e-12)
+
+
+def margin_loss(pred, target):
+    """max_{k != y} z_k - z_y per pixel (the label channel pushed down by 1e10 before the max)."""
+    onehot = torch.zeros_like(pred).scatter_(1, target.unsqueeze(1), 1.0)
+    return (pred - 1e10 * onehot).amax(1) - (pred * onehot).sum(1)
+
+
 def pixel_to_img_loss(loss, mask_background=None):
     """semseg/attacker.py:237-240."""
     if mask_background is not None:
@@ -159,12 +192,16 @@ def apgd_schedule(n_iter):
 
 def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbose=False,
                is_train=False, early_stop=False, track_loss=None, logger=None, y_target=None,
-               ignore_index=-1, x_init=None, num_classes=21, weights=None, return_pred=False):
+               ignore_index=-1, x_init=None, num_classes=21, weights=None, return_pred=False,
+               return_counts=False):
     """APGD (L-inf) with the SEA losses; returns ``(x_best, acc, loss_best, x_best_adv)``.
 
     ``return_pred=True`` (extension) appends ``pred_best``: the argmax map of
     ``x_best_adv`` as seen during the attack, which lets the SEA driver skip the re-forward of
-    every adversarial batch (tools/infer.py:82-90).
+    every adversarial batch (tools/infer.py:82-90).  ``return_counts=True`` appends ``counts_best``
+    [B,3,C] int64: the per-image intersection / target / prediction class counters of that same
+    point (what eval_performance / evalSEA derive from the prediction map), taken inside the loss
+    kernel's argmax pass -- no prediction map, no histogram launch.
 
     Mirrors semseg/attacker.py:260-571 step for step; see the module docstring for the
     kernel each block of the reference maps to."""
@@ -208,14 +245,18 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     if weights is not None and loss == "mask-ce-bal":
         w_dev = weights.to(device=device, dtype=torch.float32)  # hoisted H2D
 
-    keep_pred = verbose or return_pred
+    keep_pred = return_pred
+    keep_counts = verbose or return_counts
+
+    def result(x_best, acc, loss_best, x_best_adv, pred_best, counts_best):
+        return (x_best, acc, loss_best, x_best_adv) + ((pred_best,) if return_pred else ()) + (
+            (counts_best,) if return_counts else ())
 
     graphed = hasattr(model, "input_grad")  # graphs.GraphedModel: replayed forward / input gradient
     if graphed and hasattr(model, "attack") and not verbose and track_loss in ("ce", "ce-avg", loss):
         # the whole iteration as one CUDA graph (graphs.GraphedAttack)
-        res = model.attack(keep_pred, early_stop, n_iter).run_stage(
-            x, y, x_adv, eps, n_iter, loss, track_loss, w_dev, apgd_schedule(n_iter))
-        return res if return_pred else res[:4]
+        return result(*model.attack(keep_pred, early_stop, n_iter).run_stage(
+            x, y, x_adv, eps, n_iter, loss, track_loss, w_dev, apgd_schedule(n_iter)))
     # dropin.accelerate(model, fuse_loss=True): the model hands out its logits BEFORE the final bilinear
     # up-sampling and the loss kernel interpolates on the fly (robseg_loss_upsampled_fwd_bwd)
     lowres = getattr(model, "forward_lowres", None) if not graphed else None
@@ -236,11 +277,11 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
         if fused:
             def run(kind, **kw):
                 return ops.loss_upsampled_fwd_bwd(logits, y, kind, w_dev, **kw)
-            out = run(loss, want_grad=need_grad, want_pred=keep_pred, dlow_out=dbuf)
+            out = run(loss, want_grad=need_grad, want_pred=keep_pred, want_counts=keep_counts, dlow_out=dbuf)
         else:
             def run(kind, **kw):
                 return ops.loss_fwd_bwd(logits, y, kind, w_dev, **kw)
-            out = run(loss, want_grad=need_grad, want_pred=keep_pred, dlogits_out=dbuf)
+            out = run(loss, want_grad=need_grad, want_pred=keep_pred, want_counts=keep_counts, dlogits_out=dbuf)
         g = None
         if need_grad:
             if graphed:
@@ -278,6 +319,7 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     x_old = x_adv.clone()
     x_new = torch.empty_like(x_adv)
     pred_best = out.pred if keep_pred else None
+    counts_best = out.counts if keep_counts else None
     flags = torch.zeros([3, bs], dtype=torch.int32, device=device)
     done = torch.zeros([1], dtype=torch.int32, device=device)
     done_host = torch.zeros([1], dtype=torch.int32).pin_memory() if early_stop else None
@@ -307,11 +349,14 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
                           reduced_last, step, loss_steps, i, checks.get(i, 0), n_pxl, early_stop,
                           flags, done)
         pending = True
-        if keep_pred:
-            ops.row_select([(pred_best, out.pred, flags[0], None)], bs, device)
+        if keep_pred or keep_counts:
+            ops.row_select(([(pred_best, out.pred, flags[0], None)] if keep_pred else []) +
+                           ([(counts_best, out.counts, flags[0], None)] if keep_counts else []), bs, device)
 
         if verbose:
-            m_acc, a_acc, m_iou = compute_iou_acc(pred_best, y, n_cls, ignore_index=ignore_index)
+            # compute_iou_acc of the best point's prediction (:496-498) from its fused counters
+            m_acc, a_acc, m_iou = _iou_acc_from_counts(counts_best[:, 0].sum(0), counts_best[:, 1].sum(0),
+                                                       counts_best[:, 2].sum(0))
             logger.log(
                 "iteration: {} - best loss: {:.6f} curr loss {:.6f} - mAcc={:.2%} aAcc={:.2%} "
                 "mIoU={:.2%} - step size: {:.5f}".format(i, loss_best.sum(), track.sum(), m_acc,
@@ -331,18 +376,18 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbo
     if pending:  # the last iteration's row stores (restart copies only matter to a following step)
         ops.row_select([(x_best_adv, x_adv, flags[0], None), (x_best, x_adv, flags[1], None),
                         (grad_best, grad, flags[1], None)], bs, device)
-    if return_pred:
-        return x_best, acc, loss_best, x_best_adv, pred_best
-    return x_best, acc, loss_best, x_best_adv
+    return result(x_best, acc, loss_best, x_best_adv, pred_best, counts_best)
 
 
 def apgd_largereps(model, x, y, weights, norm="Linf", eps=8.0 / 255.0, n_iter=10, loss="ce",
                    verbose=False, n_restarts=1, log_path=None, early_stop=False, eot_iter=0,
-                   track_loss=None, use_rs=False, ignore_index=-1, num_classes=21, return_pred=False):
+                   track_loss=None, use_rs=False, ignore_index=-1, num_classes=21, return_pred=False,
+                   return_counts=False):
     """SEA's 3-stage large-eps schedule (semseg/attacker.py:662-728): iterations
     ``[.3n, .3n, rest]`` at ``[2 eps, 1.5 eps, eps]``, each stage started from the projection of
     the previous stage's lowest-accuracy point.  Returns ``(x_adv, loss_best, acc)``
-    (+ ``pred`` of ``x_adv`` with ``return_pred=True``)."""
+    (+ ``pred`` of ``x_adv`` with ``return_pred=True``; + its per-image class
+    counters [B,3,C] with ``return_counts=True``, see :func:`apgd_train`)."""
     if norm != "Linf":
         raise NotImplementedError()
     logger = Logger(log_path)
@@ -353,7 +398,7 @@ def apgd_largereps(model, x, y, weights, norm="Linf", eps=8.0 / 255.0, n_iter=10
     acc = torch.ones([x.shape[0]], device=x.device)
     x = x.detach().float().contiguous()
     x_init = None
-    loss_best = pred = None
+    loss_best = pred = counts = None
     last = len(n_iters) - 1
     for stage, (inner_it, inner_eps) in enumerate(zip(n_iters, epss)):
         if x_init is not None:
@@ -362,18 +407,47 @@ def apgd_largereps(model, x, y, weights, norm="Linf", eps=8.0 / 255.0, n_iter=10
             model, x, y, n_iter=inner_it, use_rs=use_rs, verbose=verbose, loss=loss,
             eps=inner_eps, norm=norm, logger=logger, early_stop=early_stop,
             track_loss=track_loss, y_target=None, ignore_index=ignore_index, x_init=x_init,
-            num_classes=num_classes, weights=weights, return_pred=return_pred and stage == last)
+            num_classes=num_classes, weights=weights, return_pred=return_pred and stage == last,
+            return_counts=return_counts and stage == last)
         _, acc, loss_best, x_init = res[:4]
-        if return_pred and stage == last:
-            pred = res[4]
-    if return_pred:
-        return x_init, loss_best, acc, pred
-    return x_init, loss_best, acc
+        if stage == last:
+            extra = list(res[4:])
+            pred = extra.pop(0) if return_pred else None
+            counts = extra.pop(0) if return_counts else None
+    return (x_init, loss_best, acc) + ((pred,) if return_pred else ()) + ((counts,) if return_counts else ())
 
 
-def apgd_restarts(*args, **kwargs):
-    """semseg/attacker.py:574-659 is unreachable from the SEA / PIR-AT drivers."""
-    raise NotImplementedError("apgd_restarts is outside the accelerated path")
+def apgd_restarts(model, x, y, norm="Linf", eps=8.0 / 255.0, n_iter=10, loss="ce", verbose=False,
+                  n_restarts=1, log_path=None, early_stop=False, eot_iter=0, track_loss=None,
+                  use_rs=False, ignore_index=-1):
+    """APGD with restarts (semseg/attacker.py:574-659): ``n_restarts`` independent ``apgd_train`` runs
+    over the images whose accuracy is still positive, keeping per image the adversarial point with the
+    lowest pixel accuracy (ignored pixels count as correct, :639).  Returns ``(x_adv, None, acc)``.
+    The accuracy of each run's point comes from the argmax map the attack already holds
+    (``return_pred``) instead of the reference's extra forward.  Untargeted losses only."""
+    if "targeted" in loss:
+        raise NotImplementedError("targeted losses are outside the accelerated path")
+    logger = Logger(log_path)
+    x = x.detach().float().contiguous()
+    acc = torch.ones([x.shape[0]], device=x.device)
+    x_adv = x.clone()
+    for i in range(n_restarts):
+        rows = (acc > 0).nonzero().flatten()
+        if rows.numel() == 0:
+            break
+        yr = y[rows]
+        res = apgd_train(model, x[rows], yr, n_iter=n_iter, use_rs=use_rs, verbose=verbose, loss=loss, eps=eps,
+                         norm=norm, logger=logger, early_stop=early_stop, track_loss=track_loss, y_target=None,
+                         ignore_index=ignore_index, return_pred=True)
+        x_cur, pred = res[3], res[4]
+        ok = (pred == yr) | (yr == ignore_index)
+        acc_cur = ok.float().view(rows.numel(), -1).mean(-1)
+        better = acc_cur < acc[rows]
+        x_adv[rows[better]] = x_cur[better]
+        acc[rows[better]] = acc_cur[better]
+        note = " (warning: this is only upper bound on aAcc)" if bool((yr == ignore_index).any()) else ""
+        logger.log(f"restart {i + 1} robust accuracy={acc.float().mean():.1%}{note}")
+    return x_adv, None, acc
 
 
 def L1_projection(*args, **kwargs):

@@ -4,9 +4,10 @@
     stats = run_sea(model, loader, n_cls, eps=8/255, n_iter=300, weights=bal_weights)
 
 For every batch: the three SEA attacks (``mask-ce-bal``, ``mask-ce-avg``, ``js-avg``) through
-``apgd_largereps``; the argmax map of each adversarial point comes back from the attack
-(``return_pred``) instead of a D2H copy of ``x_adv`` + a later re-forward (tools/infer.py:151,82-90);
-exact int64 per-image counters are accumulated on the device (``robseg_pixel_hist``).  With
+``apgd_largereps``; the exact int64 per-image class counters of each adversarial point come back from
+the attack itself (``return_counts``: taken in the loss kernel's argmax pass, robseg_loss_fwd_bwd_counts)
+instead of a D2H copy of ``x_adv``, a later re-forward (tools/infer.py:151,82-90) and 2*C masked
+reductions (:94-116) -- no prediction map and no histogram launch on this route.  With
 ``torch.distributed`` initialised every rank attacks its own contiguous shard of the loader's batches
 and ONE int64 all-reduce merges the counters.  The aggregation is the same
 code path as ``evalSEA``: per-attack mAcc / aAcc / mIoU (float32 finaliser of tools/infer.py:99-116),
@@ -97,16 +98,14 @@ def run_sea(model, loader, n_cls, eps=8.0 / 255.0, n_iter=300, weights=None, los
             out = model(x)
         if out.dtype not in (torch.float32, torch.bfloat16):
             out = out.float()
-        p0 = ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_pred=True, want_stats=False).pred
-        c = ops.pixel_hist(p0, y, n_cls)
-        clean_cnt.append(torch.stack([c["inter"], c["tgt"], c["prd"]]))
+        c0 = ops.loss_fwd_bwd(out, y, "argmax", want_grad=False, want_stats=False, want_counts=True).counts
+        clean_cnt.append(c0.permute(1, 0, 2))  # [B,3,C] -> [3,B,C]
         del out
         for a, loss in enumerate(losses):
-            x_adv, _, _, pred = attacker.apgd_largereps(
+            x_adv, _, _, cnt = attacker.apgd_largereps(
                 model, x, y, weights, norm="Linf", eps=eps, n_iter=n_iter, loss=loss, track_loss="ce-avg",
-                use_rs=True, early_stop=True, num_classes=n_cls, return_pred=True)
-            c = ops.pixel_hist(pred, y, n_cls)
-            per_loss[a].append(torch.stack([c["inter"], c["tgt"], c["prd"]]))
+                use_rs=True, early_stop=True, num_classes=n_cls, return_counts=True)
+            per_loss[a].append(cnt.permute(1, 0, 2))
             if keep_adv:
                 advs[a].append(x_adv)
     zero = torch.zeros((3, 0, n_cls), dtype=torch.int64, device=dev)

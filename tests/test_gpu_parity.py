@@ -55,7 +55,10 @@ SHAPES = [(2, 21, 32, 32), (2, 7, 5, 6), (1, 64, 16, 24), (1, 150, 24, 24), (2, 
           (1, 21, 33, 37), (1, 151, 13, 11), (3, 2, 8, 8), (1, 256, 8, 8), (1, 300, 6, 6),
           # odd H*W (rows only 4-byte aligned): the strided generic kernel at 4 / 2 pixels per lane, tiles
           # crossing the image end, images smaller than one tile
-          (2, 21, 47, 43), (1, 40, 25, 25), (3, 5, 7, 5), (2, 27, 19, 27), (1, 55, 11, 13)]
+          (2, 21, 47, 43), (1, 40, 25, 25), (3, 5, 7, 5), (2, 27, 19, 27), (1, 55, 11, 13),
+          # H*W = 2 mod 4 (rows 8-byte aligned: the over-fetch phases alternate 0 / 2), the last chunk of the
+          # tensor cut short, one pixel per lane with a single stage (C = 120)
+          (2, 21, 6, 7), (1, 9, 10, 15), (1, 3, 5, 5), (1, 120, 9, 9)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -76,9 +79,10 @@ def test_loss_kernel_vs_oracle_fp32(mods, shape, kind):
 
 
 def test_loss_kernel_voc_shape_generic_paths_agree(mods, monkeypatch):
-    """The reference's PASCAL-VOC shape (473 x 473 crops, 21 classes: odd H*W, no TMA): the strided
-    generic kernels (4 and 2 pixels per lane) and the one-pixel kernel give the same argmax map and
-    counts exactly and the same losses / gradients to rounding; properties at full size."""
+    """The reference's PASCAL-VOC shape (473 x 473 crops, 21 classes: odd H*W, no TMA): the 16-byte
+    over-fetch kernels (4, 2, 1 pixels per lane), the 4-byte-copy strided kernels (4 and 2 pixels per lane)
+    and the one-pixel kernel give the same argmax map and counts exactly and the same losses / gradients to
+    rounding; properties at full size."""
     B, C, S = 6, 21, 473
     g = torch.Generator(device=dev()).manual_seed(3)
     z = 3 * torch.randn(B, C, S, S, device=dev(), generator=g)
@@ -87,13 +91,18 @@ def test_loss_kernel_voc_shape_generic_paths_agree(mods, monkeypatch):
     w = 0.5 + torch.rand(C, device=dev(), generator=g)
     for kind in ("mask-ce-bal", "js-avg"):
         outs = []
+        for ovf in ("4", "2", "1"):  # robseg_loss_fwd_bwd's over-fetch path at each width
+            monkeypatch.setenv("ROBSEG_LOSS_GENERIC_OVF", ovf)
+            outs.append(mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_loss_pix=True))
+        monkeypatch.setenv("ROBSEG_LOSS_GENERIC_OVF", "0")  # the 4-byte-copy kernels
         for vec in ("4", "2", "1"):
             monkeypatch.setenv("ROBSEG_LOSS_GENERIC_VEC", vec)
             outs.append(mods.ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_loss_pix=True))
         monkeypatch.delenv("ROBSEG_LOSS_GENERIC_VEC")
-        ref = outs[2]
+        monkeypatch.delenv("ROBSEG_LOSS_GENERIC_OVF")
+        ref = outs[-1]
         assert torch.equal(ref.pred, z.argmax(1))
-        for o in outs[:2]:
+        for o in outs[:-1]:
             assert torch.equal(o.pred, ref.pred) and torch.equal(o.correct, ref.correct) and torch.equal(o.valid, ref.valid)
             assert rel(o.dlogits.cpu().numpy(), ref.dlogits.cpu().numpy()) <= 2e-6
             assert rel(o.loss_pix.cpu().numpy(), ref.loss_pix.cpu().numpy()) <= 2e-6
@@ -615,6 +624,38 @@ def _return_pred_case(mods):
         assert torch.equal(x_adv2, x_adv) and torch.equal(acc2, acc) and torch.equal(lb2, lb)
 
 
+def test_apgd_restarts_keeps_the_lowest_accuracy_point(mods):
+    """apgd_restarts (semseg/attacker.py:574-659): every returned point lies in the eps-ball, its accuracy is
+    what a re-forward measures (ignored pixels correct, :639), it never exceeds the accuracy of a single run,
+    and images already at zero accuracy are not attacked again."""
+    C = 6
+    model = mods.consumers.TinySegNet(C, seed=4).to(dev()).eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(4, 3, 24, 24, generator=g).to(dev())
+    with torch.no_grad():
+        y = model(x).argmax(1)
+    y[1, :3] = -1
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        torch.manual_seed(5)
+        x1, _, acc1 = mods.attacker.apgd_restarts(model, x, y, eps=8 / 255, n_iter=6, loss="mask-ce-avg",
+                                                  track_loss="ce-avg", n_restarts=1, use_rs=True)
+        torch.manual_seed(5)
+        x3, none, acc3 = mods.attacker.apgd_restarts(model, x, y, eps=8 / 255, n_iter=6, loss="mask-ce-avg",
+                                                     track_loss="ce-avg", n_restarts=3, use_rs=True)
+        assert none is None
+        assert float((x3 - x).abs().max()) <= 8 / 255 + 1e-6 and float(x3.min()) >= 0 and float(x3.max()) <= 1
+        assert bool((acc3 <= acc1).all())  # the first restart is the same run (same seed)
+        again = model(x3.detach().requires_grad_()).argmax(1)
+        ok = (again == y) | (y == -1)
+        assert torch.equal(acc3, ok.float().flatten(1).mean(1))
+    finally:
+        torch.backends.cudnn.deterministic = det
+    with pytest.raises(NotImplementedError):
+        mods.attacker.apgd_restarts(model, x, y, loss="dlr-targeted")
+
+
 def test_verbose_path_and_bf16_consumer(mods, capsys):
     """verbose=True keeps the reference's per-iteration mAcc/aAcc/mIoU report (attacker.py:500-515);
     a consumer that emits bf16 logits runs through the bf16 kernel."""
@@ -677,6 +718,9 @@ def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
                                    (2, 7, 16, 16, 32, 32), (2, 7, 16, 16, 128, 128), (1, 3, 7, 9, 14, 18),
                                    (1, 3, 5, 61, 10, 122), (1, 2, 33, 32, 66, 64), (1, 2, 3, 70, 24, 560),
                                    (1, 2, 1, 1, 8, 8), (1, 2, 1, 1, 2, 2), (1, 3, 70, 5, 140, 10), (1, 2, 40, 3, 320, 24),
+                                   # x2 with even sides: the 2x2-cells-per-thread forward (borders, the plane loop with
+                                   # its prefetch: more planes than plane groups, a single 2x2 plane)
+                                   (3, 4, 2, 2, 4, 4), (1, 2500, 4, 4, 8, 8), (2, 9, 6, 10, 12, 20), (1, 5, 64, 64, 128, 128),
                                    # non-integer ratios of the reference's 473x473 PASCAL-VOC crops (119 -> 473 logits,
                                    # 14 / 29 / 59 -> 119 pyramid) and other walk-down gather cases
                                    (2, 5, 119, 119, 473, 473), (1, 3, 14, 14, 119, 119), (1, 3, 29, 29, 59, 59),

@@ -382,3 +382,32 @@ def test_run_sea_shards_the_loader_without_touching_foreign_batches(pkg):
     batches = [(torch.zeros(2, 3, 2, 2), torch.zeros(2, 2, 2)) for _ in range(5)]
     sizes, lo_b, own = sea._own_batches(batches, 1, 2, -1)
     assert sizes == [2] * 5 and lo_b == 3 and len(own) == 2
+
+
+def test_margin_type_losses_follow_their_definitions(mods):
+    """dlr_loss / dlr_loss_targeted / margin_loss (name parity with semseg/attacker.py:123-141,176-184):
+    checked element by element against the published definitions written out with Python sorts."""
+    A = mods.attacker
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(11, 7, generator=g, dtype=torch.float64)
+    y = torch.randint(0, 7, (11,), generator=g)
+    t = torch.randint(0, 7, (11,), generator=g)
+    y[0] = int(x[0].argmax())  # label = top class: the runner-up enters the numerator
+    d, dt = A.dlr_loss(x, y), A.dlr_loss_targeted(x, y, t)
+    for i in range(11):
+        row = x[i].tolist()
+        s = sorted(row)
+        other = s[-2] if row.index(s[-1]) == int(y[i]) else s[-1]
+        assert abs(float(d[i]) - (-(row[y[i]] - other) / (s[-1] - s[-3] + 1e-12))) < 1e-12
+        assert abs(float(dt[i]) - (-(row[y[i]] - row[t[i]]) / (s[-1] - 0.5 * (s[-3] + s[-4]) + 1e-12))) < 1e-12
+    z = torch.randn(2, 5, 3, 4, generator=g)
+    lab = torch.randint(0, 5, (2, 3, 4), generator=g)
+    m = A.margin_loss(z, lab)
+    assert m.shape == lab.shape
+    for b, i, j in ((0, 0, 0), (1, 2, 3), (0, 1, 2)):
+        col = z[b, :, i, j].tolist()
+        k = int(lab[b, i, j])
+        assert abs(float(m[b, i, j]) - (max(v for c, v in enumerate(col) if c != k) - col[k])) < 1e-5
+    z.requires_grad_(True)
+    A.margin_loss(z, lab).sum().backward()  # differentiable, like the reference's
+    assert z.grad is not None and float(z.grad.abs().sum()) > 0
