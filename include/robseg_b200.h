@@ -118,9 +118,10 @@ int robseg_loss_upsampled_fwd_bwd(const float* low, const int64_t* labels, const
  * tools/infer.py:86-116 and evalSEA, tools/worse_only.py:30-66, derive from a prediction map) taken
  * in the kernel's argmax pass, so neither the int64 prediction map nor a robseg_pixel_hist launch
  * is needed to score an adversarial point:
- *   counts [B,3,C] int64 (zeroed by the call):  [b,0,c] = #{pred == label == c},
+ *   counts [B,3,C] int64 (written by the call): [b,0,c] = #{pred == label == c},
  *   [b,1,c] = #{label == c}, [b,2,c] = #{pred == c, label valid}; ignored pixels add nothing.
- * Exact (integer reductions), identical to robseg_pixel_hist on the pred this call would return.
+ * Exact (integer reductions into 8 copies held in the workspace -- the ..._workspace_bytes functions account
+ * for them -- added up by a small kernel), identical to robseg_pixel_hist on the pred this call would return.
  * All other arguments as in robseg_loss_fwd_bwd / robseg_loss_upsampled_fwd_bwd.
  */
 int robseg_loss_fwd_bwd_counts(const void* logits, int dtype, const int64_t* labels,

@@ -102,6 +102,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // reduction); whatever is left after two rounds -- nothing on a coherent map, nothing on a two-class boundary row --
 // issues its own reduction.  A pixel whose label is ignored contributes nothing (its prediction is ignored too,
 // attacker.py:20).  Must be called by all 32 lanes.
+// The reductions go to one of kCountReplicas copies of the [B][3][C] block (copy = blockIdx.x mod kCountReplicas, in the
+// caller's workspace): all CTAs work on the same image at the same time, and with a single copy the L2 atomic units
+// serialise on that image's 3*C addresses (uniformly random labels: +13 % on the loss kernel).  A small kernel adds the
+// copies into the caller's counts tensor afterwards (launch_counts_fold).
+constexpr int kCountReplicas = 8;
+int launch_counts_fold(const unsigned long long* replicas, int B, int C, int64_t* counts, cudaStream_t stream);
+
 __device__ __forceinline__ void count_keys(unsigned long long* arr, bool valid, int key) {
   const int lane = threadIdx.x & 31;
   unsigned left = __ballot_sync(0xffffffffu, valid);

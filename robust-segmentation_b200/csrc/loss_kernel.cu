@@ -42,7 +42,7 @@ struct LossParams {
   float* loss_pix;
   int64_t* pred;
   float4* partials;
-  unsigned long long* counts;  // [B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
+  unsigned long long* counts;  // [kCountReplicas][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
   int64_t HW;
   int kind, ignore_index, B, C;
   int tiles_per_img, num_tiles, n_slots, n_consumers;
@@ -169,7 +169,7 @@ struct TileCls {
 };
 template <int VEC>
 __device__ __forceinline__ void count_tile(const LossParams& p, const TileCls<VEC>& k) {
-  unsigned long long* cnt = p.counts + (size_t)k.b * 3 * p.C;
+  unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (kCountReplicas - 1)) * p.B + k.b) * 3 * p.C;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) count_pixel(cnt, p.C, k.t[j] >= 0, k.t[j], k.q[j]);
 }
@@ -1139,6 +1139,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// counts[b][i] = sum over the replicas (see kCountReplicas); grid B, i < 3*C
+__global__ void __launch_bounds__(256)
+    counts_fold_kernel(const unsigned long long* __restrict__ rep, int B, int n, long long* __restrict__ counts) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int r = 0; r < kCountReplicas; ++r) s += rep[((size_t)r * B + b) * n + i];
+    counts[(size_t)b * n + i] = (long long)s;
+  }
+}
+int launch_counts_fold(const unsigned long long* replicas, int B, int C, int64_t* counts, cudaStream_t stream) {
+  counts_fold_kernel<<<B, 256, 0, stream>>>(replicas, B, 3 * C, reinterpret_cast<long long*>(counts));
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+static size_t count_replica_bytes(int B, int C) { return (size_t)kCountReplicas * B * 3 * C * sizeof(int64_t); }
+
 // ---- host side -----------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -1358,10 +1376,13 @@ int launch_loss_finalize(const float4* partials, int B, int tiles_per_img, const
 
 using namespace robseg;
 
+static size_t loss_partial_bytes(int B, int64_t HW) {
+  return ((size_t)tiles_upper_bound(B, HW) * sizeof(float4) + 255) / 256 * 256;
+}
 extern "C" size_t robseg_loss_workspace_bytes(int B, int C, int64_t HW, int dtype) {
-  (void)C, (void)dtype;
-  if (B <= 0 || HW <= 0) return 0;
-  return (size_t)tiles_upper_bound(B, HW) * sizeof(float4);
+  (void)dtype;
+  if (B <= 0 || HW <= 0 || C <= 0) return 0;
+  return loss_partial_bytes(B, HW) + count_replica_bytes(B, C);  // per-tile partials | counter replicas
 }
 
 static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* labels,
@@ -1388,9 +1409,10 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
   p.partials = static_cast<float4*>(workspace);
   p.HW = HW, p.kind = loss_kind, p.ignore_index = ignore_index, p.B = B, p.C = C;
   p.inv_hw = (float)(1.0 / (double)HW);
-  p.counts = reinterpret_cast<unsigned long long*>(counts);
-  if (counts != nullptr)
-    ROBSEG_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * C * sizeof(int64_t), stream));
+  if (counts != nullptr) {
+    p.counts = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + loss_partial_bytes(B, HW));
+    ROBSEG_CUDA(cudaMemsetAsync(p.counts, 0, count_replica_bytes(B, C), stream));
+  }
 
   const int esize = dtype == ROBSEG_F32 ? 4 : 2;
   auto al16 = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
@@ -1417,6 +1439,10 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
                              : launch_generic<__nv_bfloat16>(p, stream, &tiles_per_img);
   }
   if (rc != 0) return rc;
+  if (counts != nullptr) {
+    rc = launch_counts_fold(p.counts, B, C, counts, stream);
+    if (rc != 0) return rc;
+  }
   if (loss_img || track_img || correct_img || valid_img) {
     loss_finalize_kernel<<<B, 256, 0, stream>>>(p.partials, tiles_per_img, grad_scale,
                                                 1.0 / (double)HW, loss_img, track_img,

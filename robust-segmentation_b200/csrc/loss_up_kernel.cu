@@ -41,7 +41,7 @@ struct LossUpParams {
   float4* contrib;  // [B][h+1][C][w+1] corner contributions (a,b,c,d), or nullptr (no gradient)
   int64_t* pred;
   float4* partials;
-  unsigned long long* counts;  // [B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
+  unsigned long long* counts;  // [kCountReplicas][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
   int kind, ignore_index, B, C, h, w, H, W;
   int groups_x, tiles_per_img, num_tiles;
   float inv_hw;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
     }
 
     if (p.counts != nullptr) {  // warp-uniform; pixels outside the image carry y = ignore_index
-      unsigned long long* cnt = p.counts + (size_t)b * 3 * C;
+      unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (kCountReplicas - 1)) * p.B + b) * 3 * C;
 #pragma unroll
       for (int r = 0; r < R; ++r)
         count_pixel(cnt, C, (y[r] != p.ignore_index) && (y[r] >= 0) && (y[r] < C), y[r], amx[r]);
@@ -419,10 +419,11 @@ static int launch_up(LossUpParams p, cudaStream_t stream) {
 
 using namespace robseg;
 
+static size_t up_replica_bytes(int B, int C) { return (size_t)kCountReplicas * B * 3 * C * sizeof(int64_t); }
 extern "C" size_t robseg_loss_upsampled_workspace_bytes(int B, int C, int h, int w, int H, int W) {
   if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || H % h != 0) return 0;
   const int R = H / h;
-  return partial_bytes(B, h, W, R) + contrib_bytes(B, C, h, w);
+  return partial_bytes(B, h, W, R) + contrib_bytes(B, C, h, w) + up_replica_bytes(B, C);  // partials | corners | counters
 }
 
 static int loss_upsampled_impl(const float* low, const int64_t* labels, const float* class_w,
@@ -451,12 +452,18 @@ static int loss_upsampled_impl(const float* low, const int64_t* labels, const fl
                         : nullptr;
   p.kind = loss_kind, p.ignore_index = ignore_index, p.B = B, p.C = C, p.h = h, p.w = w, p.H = H, p.W = W;
   p.inv_hw = (float)(1.0 / ((double)H * W));
-  p.counts = reinterpret_cast<unsigned long long*>(counts);
-  if (counts != nullptr)
-    ROBSEG_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * C * sizeof(int64_t), stream));
+  if (counts != nullptr) {
+    p.counts = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + partial_bytes(B, h, W, R) +
+                                                     contrib_bytes(B, C, h, w));
+    ROBSEG_CUDA(cudaMemsetAsync(p.counts, 0, up_replica_bytes(B, C), stream));
+  }
   int rc = R == 16 ? launch_up<16>(p, stream) : R == 8 ? launch_up<8>(p, stream)
            : R == 4 ? launch_up<4>(p, stream) : launch_up<2>(p, stream);
   if (rc != 0) return rc;
+  if (counts != nullptr) {
+    rc = launch_counts_fold(p.counts, B, C, counts, stream);
+    if (rc != 0) return rc;
+  }
   if (want_grad) {
     const int64_t total = (int64_t)B * C * h * w;
     int grid = (int)((total + 255) / 256);

@@ -149,7 +149,7 @@ def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=N
         else:
             rc = lib.robseg_loss_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_fwd_bwd")
-    _lib.count(2 if want_stats else 1)
+    _lib.count((2 if want_stats else 1) + (1 if want_counts else 0))
     if want_stats:
         return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlogits, pred, loss_pix, counts)
     return LossOut(None, None, None, None, dlogits, pred, loss_pix, counts)
@@ -223,7 +223,7 @@ def loss_upsampled_fwd_bwd(low, labels, kind, weights=None, grad_scale=None, wan
         else:
             rc = lib.robseg_loss_upsampled_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_upsampled_fwd_bwd")
-    _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0))
+    _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0) + (1 if want_counts else 0))
     if want_stats:
         return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlow, pred, None, counts)
     return LossOut(None, None, None, None, dlow, pred, None, counts)

@@ -19,6 +19,14 @@ for B, C, H, W in [(2, 21, 32, 32), (1, 150, 24, 40), (1, 151, 13, 11), (1, 64, 
             ops.loss_fwd_bwd(z, y, kind, w, want_pred=True, want_loss_pix=kind != "argmax", want_grad=kind != "argmax")
             ops.loss_fwd_bwd(z.bfloat16(), y, kind, w, want_grad=kind != "argmax")
             for k in env: os.environ.pop(k)
+    # round 2: class counters in the argmax pass, over-fetch generic path at every width, the 4-byte-copy kernels
+    for env in ({}, {"ROBSEG_LOSS_GENERIC_OVF": "4"}, {"ROBSEG_LOSS_GENERIC_OVF": "1"}, {"ROBSEG_LOSS_GENERIC_OVF": "0"},
+                {"ROBSEG_LOSS_G": "2"}):
+        os.environ.update(env)
+        ops.loss_fwd_bwd(z, y, "mask-ce-avg", w, want_pred=True, want_counts=True)
+        ops.loss_fwd_bwd(z, y, "argmax", want_grad=False, want_stats=False, want_counts=True)
+        ops.loss_fwd_bwd(z.bfloat16(), y, "js-avg", w, want_counts=True)
+        for k in env: os.environ.pop(k)
     pred = z.argmax(1)
     ops.pixel_hist(pred, y, C, want_hist=True)
     ops.pixel_hist(pred, y, C)
@@ -29,7 +37,9 @@ d = torch.zeros_like(x); ops.pgd_step(x, d, torch.randn_like(x), 0.01, 0.03, mas
 for shp in [(1, 3, 8, 8, 32, 32), (1, 2, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1, 2, 2, 2, 32, 32), (1, 35, 33, 31, 132, 124),
             (1, 3, 7, 9, 14, 18), (1, 2, 5, 61, 10, 122), (2, 3, 16, 16, 128, 128), (1, 2, 3, 5, 48, 80), (1, 2, 1, 1, 16, 16),
             (1, 2, 6, 6, 16, 16), (1, 2, 33, 32, 66, 64), (1, 2, 30, 30, 119, 119), (1, 2, 14, 14, 119, 119),
-            (1, 2, 59, 60, 119, 121), (1, 1, 70, 5, 100, 9)]:
+            (1, 2, 59, 60, 119, 121), (1, 1, 70, 5, 100, 9),
+            # exact x2 with even sides: the 2x2-cells-per-thread kernels (borders, one 2x2 plane, plane loop)
+            (2, 3, 16, 16, 32, 32), (1, 2, 6, 10, 12, 20), (3, 4, 2, 2, 4, 4), (1, 700, 4, 4, 8, 8)]:
     a = torch.randn(*shp[:4], generator=g).to(dev).requires_grad_()
     o = ops.upsample_bilinear(a, shp[4:]); o.sum().backward()
 # gradient read in place from a channel slice of a concatenated gradient (strided planes)
@@ -50,6 +60,15 @@ model = cons.TinySegNet(7, seed=1).to(dev).eval()
 xx = torch.rand(2, 3, 16, 16, generator=g).to(dev)
 yy = model(xx).argmax(1)
 att.apgd_largereps(model, xx, yy, None, eps=8 / 255, n_iter=10, loss="mask-ce-avg", track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=7, return_pred=True)
+att.apgd_largereps(model, xx, yy, None, eps=8 / 255, n_iter=10, loss="js-avg", track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=7, return_counts=True)
+gm = import_module("robseg_b200.graphs").GraphedModel(model, xx)  # control-block step / bookkeeping kernels under graph replay
+att.apgd_largereps(gm, xx, yy, None, eps=8 / 255, n_iter=10, loss="mask-ce-avg", track_loss="ce-avg", use_rs=True, early_stop=True, num_classes=7, return_counts=True)
+# fused up-sampling loss (x2 / x4 / x16, gradient + counters)
+for B, C, h, w_, R in [(2, 21, 8, 8, 4), (1, 150, 3, 5, 16), (1, 33, 6, 6, 2), (1, 7, 5, 9, 8)]:
+    low = (3 * torch.randn(B, C, h, w_, generator=g)).to(dev)
+    yl = torch.randint(-1, C, (B, h * R, w_ * R), generator=g).to(dev)
+    ops.loss_upsampled_fwd_bwd(low, yl, "mask-ce-bal", None, want_pred=True, want_counts=True)
+    ops.loss_upsampled_fwd_bwd(low, yl, "argmax", want_grad=False, want_counts=True)
 inter = torch.randint(0, 9, (3, 4, 7)).to(dev); ops.sea_worst_acc(inter, inter + 1)
 torch.cuda.synchronize()
 print("sanitize pass done")

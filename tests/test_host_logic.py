@@ -40,7 +40,8 @@ def test_library_exports_every_declared_symbol(mods):
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.robseg_version() == mods.lib.ABI_VERSION
-    assert lib.robseg_loss_workspace_bytes(16, 150, 512 * 512, 0) == 16 * (512 * 512 // 32) * 16
+    # per-tile partials (one float4 per 32 pixels, upper bound) + 8 copies of the [B,3,C] int64 class counters
+    assert lib.robseg_loss_workspace_bytes(16, 150, 512 * 512, 0) == 16 * (512 * 512 // 32) * 16 + 8 * 16 * 3 * 150 * 8
     syms = subprocess.run(["nm", "-D", "--defined-only", mods.lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (robseg_[a-z0-9_]+)", syms))
     assert declared <= exported
