@@ -102,12 +102,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // reduction); whatever is left after two rounds -- nothing on a coherent map, nothing on a two-class boundary row --
 // issues its own reduction.  A pixel whose label is ignored contributes nothing (its prediction is ignored too,
 // attacker.py:20).  Must be called by all 32 lanes.
-// The reductions go to one of kCountReplicas copies of the [B][3][C] block (copy = blockIdx.x mod kCountReplicas, in the
-// caller's workspace): all CTAs work on the same image at the same time, and with a single copy the L2 atomic units
-// serialise on that image's 3*C addresses (uniformly random labels: +13 % on the loss kernel).  A small kernel adds the
-// copies into the caller's counts tensor afterwards (launch_counts_fold).
-constexpr int kCountReplicas = 8;
-int launch_counts_fold(const unsigned long long* replicas, int B, int C, int64_t* counts, cudaStream_t stream);
+// The reductions go to one of R copies of the [B][3][C] block (copy = blockIdx.x mod R, in the caller's workspace):
+// all CTAs work on the same image at the same time, and with a single copy the L2 atomic units serialise on that
+// image's 3*C addresses (uniformly random labels: +13 % on the loss kernel at C = 150, far more at C = 21).  R grows as
+// C shrinks so that an image always spreads over >= ~2000 addresses.  A small kernel adds the copies into the caller's
+// counts tensor afterwards (launch_counts_fold).
+__host__ __device__ inline int count_replicas(int C) {
+  int r = 8;
+  while (r < 128 && r * 3 * C < 2048) r <<= 1;
+  return r;
+}
+int launch_counts_fold(const unsigned long long* replicas, int R, int B, int C, int64_t* counts, cudaStream_t stream);
+int launch_counts_zero(unsigned long long* replicas, size_t bytes, cudaStream_t stream);  // bytes: multiple of 16
 
 __device__ __forceinline__ void count_keys(unsigned long long* arr, bool valid, int key) {
   const int lane = threadIdx.x & 31;
@@ -127,6 +133,33 @@ __device__ __forceinline__ void count_pixel(unsigned long long* cnt, int C, bool
   count_keys(cnt + C, valid, t);              // target
   count_keys(cnt + 2 * C, valid, q);          // prediction (only where the label is valid)
   count_keys(cnt, valid && t == q, t);        // intersection
+}
+// All N pixels of every lane at once (t[j] < 0: pixel not counted).  Fast path for the common case on real label
+// maps -- the whole warp tile lies inside one region, i.e. every (label, prediction) pair is the same: one compare
+// per pixel, one vote, and lane 0 issues the (at most three) reductions for 32*N pixels.  The general path above costs
+// ~45 instructions per pixel slot, which an issue-bound launch (C = 21: ~1500 instructions per tile) feels: +18 %.
+template <int N>
+__device__ __forceinline__ void count_pixels(unsigned long long* cnt, int C, const int (&t)[N], const int (&q)[N]) {
+  if (C < 32768) {
+    int key[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) key[j] = t[j] >= 0 ? ((t[j] << 16) | q[j]) : -1;
+    const int k0 = __shfl_sync(0xffffffffu, key[0], 0);
+    bool same = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) same = same && key[j] == k0;
+    if (__all_sync(0xffffffffu, same)) {
+      if ((threadIdx.x & 31) == 0 && k0 >= 0) {
+        const int tt = k0 >> 16, qq = k0 & 0xffff;
+        atomicAdd(cnt + C + tt, (unsigned long long)(32 * N));
+        atomicAdd(cnt + 2 * C + qq, (unsigned long long)(32 * N));
+        if (tt == qq) atomicAdd(cnt + tt, (unsigned long long)(32 * N));
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) count_pixel(cnt, C, t[j] >= 0, t[j], q[j]);
 }
 
 template <typename T>

@@ -42,9 +42,9 @@ struct LossParams {
   float* loss_pix;
   int64_t* pred;
   float4* partials;
-  unsigned long long* counts;  // [kCountReplicas][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
+  unsigned long long* counts;  // [n_rep][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
   int64_t HW;
-  int kind, ignore_index, B, C;
+  int kind, ignore_index, B, C, n_rep;
   int tiles_per_img, num_tiles, n_slots, n_consumers;
   float inv_hw;
 };
@@ -169,9 +169,8 @@ struct TileCls {
 };
 template <int VEC>
 __device__ __forceinline__ void count_tile(const LossParams& p, const TileCls<VEC>& k) {
-  unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (kCountReplicas - 1)) * p.B + k.b) * 3 * p.C;
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) count_pixel(cnt, p.C, k.t[j] >= 0, k.t[j], k.q[j]);
+  unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (p.n_rep - 1)) * p.B + k.b) * 3 * p.C;
+  count_pixels<VEC>(cnt, p.C, k.t, k.q);
 }
 
 // The labels of a warp tile (int64 -> int), ignore_index for pixels beyond the image.  Separate from
@@ -888,6 +887,8 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
   const int stride = gridDim.x * W;
   int tile = blockIdx.x * W + warp;
   int k = 0;
+  TileCls<1> prev, now;
+  bool pending = false;
   if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
   for (; tile < p.num_tiles; tile += stride) {
     float* cur = bufs + (size_t)k * stage_elems;
@@ -907,8 +908,8 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
     __syncwarp();
     const int tin = tile % p.tiles_per_img;
     int y[1];
-    TileCls<1> cls;
-    TileCls<1>* out = p.counts != nullptr ? &cls : nullptr;
+    if (pending) count_tile<1>(p, prev);  // one tile late: see TileCls
+    TileCls<1>* out = p.counts != nullptr ? &now : nullptr;
     if ((int64_t)(tin + 1) * 32 <= p.HW) {
       tile_labels<1, false, false>(p, tile, lane, y);
       process_tile<float, 1, 1, false>(p, cur, tile, lane, 0, PairXch{}, y, out);
@@ -916,9 +917,10 @@ __global__ void __launch_bounds__(256) loss_generic_f32_kernel(const LossParams 
       tile_labels<1, true, false>(p, tile, lane, y);
       process_tile<float, 1, 1, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
     }
-    if (out != nullptr) count_tile<1>(p, cls);
+    if (out != nullptr) prev = now, pending = true;
     __syncwarp();
   }
+  if (pending) count_tile<1>(p, prev);
 }
 
 // Wider tiles for the same case: [C][32*VEC] stages filled with 4-byte copies (lane L copies
@@ -959,6 +961,8 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
   const int stride = gridDim.x * W;
   int tile = blockIdx.x * W + warp;
   int k = 0;
+  TileCls<VEC> prev, now;
+  bool pending = false;
   if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
   for (; tile < p.num_tiles; tile += stride) {
     float* cur = bufs + (size_t)k * stage_elems;
@@ -978,8 +982,8 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
     __syncwarp();
     const int tin = tile % p.tiles_per_img;
     int y[VEC];
-    TileCls<VEC> cls;
-    TileCls<VEC>* out = p.counts != nullptr ? &cls : nullptr;
+    if (pending) count_tile<VEC>(p, prev);  // one tile late: see TileCls
+    TileCls<VEC>* out = p.counts != nullptr ? &now : nullptr;
     if ((int64_t)(tin + 1) * ROW <= p.HW) {
       tile_labels<VEC, false, true>(p, tile, lane, y);
       process_tile<float, VEC, 1, false, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
@@ -987,9 +991,10 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
       tile_labels<VEC, true, true>(p, tile, lane, y);
       process_tile<float, VEC, 1, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out);
     }
-    if (out != nullptr) count_tile<VEC>(p, cls);
+    if (out != nullptr) prev = now, pending = true;
     __syncwarp();
   }
+  if (pending) count_tile<VEC>(p, prev);
 }
 
 // The same case with 16-byte copies (one 4-byte cp.async per logit kept the copy pipe busy
@@ -1052,6 +1057,8 @@ __global__ void __launch_bounds__(256) loss_generic_ovf_kernel(const LossParams 
   const int stride = gridDim.x * W;
   int tile = blockIdx.x * W + warp;
   int k = 0;
+  TileCls<VEC> prev, now;
+  bool pending = false;
   if (K == 2 && tile < p.num_tiles) issue(tile, bufs);
   for (; tile < p.num_tiles; tile += stride) {
     float* cur = bufs + (size_t)k * stage_elems;
@@ -1075,13 +1082,14 @@ __global__ void __launch_bounds__(256) loss_generic_ovf_kernel(const LossParams 
     }
     __syncwarp();
     const int ph0 = (int)(row0(tile) & 3);
-    TileCls<VEC> cls;
-    TileCls<VEC>* out = p.counts != nullptr ? &cls : nullptr;
+    if (pending) count_tile<VEC>(p, prev);  // one tile late: see TileCls
+    TileCls<VEC>* out = p.counts != nullptr ? &now : nullptr;
     if (full) process_tile<float, VEC, 1, false, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
     else process_tile<float, VEC, 1, true, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
-    if (out != nullptr) count_tile<VEC>(p, cls);
+    if (out != nullptr) prev = now, pending = true;
     __syncwarp();
   }
+  if (pending) count_tile<VEC>(p, prev);
 }
 
 template <typename T>
@@ -1090,6 +1098,8 @@ __global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * p.C * 32;
   const T* logits = reinterpret_cast<const T*>(p.logits);
+  TileCls<1> prev, now;
+  bool pending = false;
   for (int tile = blockIdx.x * W + warp; tile < p.num_tiles; tile += gridDim.x * W) {
     const int b = tile / p.tiles_per_img;
     const int64_t px = (int64_t)(tile - b * p.tiles_per_img) * 32 + lane;
@@ -1101,12 +1111,13 @@ __global__ void __launch_bounds__(256) loss_generic_kernel(const LossParams p) {
     __syncwarp();
     int y[1];
     tile_labels<1, true, false>(p, tile, lane, y);
-    TileCls<1> cls;
-    TileCls<1>* out = p.counts != nullptr ? &cls : nullptr;
+    if (pending) count_tile<1>(p, prev);  // one tile late: see TileCls
+    TileCls<1>* out = p.counts != nullptr ? &now : nullptr;
     process_tile<T, 1, 1, true>(p, stage, tile, lane, 0, PairXch{}, y, out);
-    if (out != nullptr) count_tile<1>(p, cls);
+    if (out != nullptr) prev = now, pending = true;
     __syncwarp();
   }
+  if (pending) count_tile<1>(p, prev);
 }
 
 // ---- fixed-order per-image reduction of the tile partials ----------------------------------
@@ -1139,23 +1150,53 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// counts[b][i] = sum over the replicas (see kCountReplicas); grid B, i < 3*C
+// counts[b][i] = sum over the R replicas (see count_replicas).  Grid (B, ceil(3C / 32)), 8 warps: warp w adds replicas
+// w, w+8, ... for 32 consecutive counters (coalesced 256-byte reads, R/8 independent loads per lane), then the warps'
+// partial sums meet in shared memory.  (One thread per counter walking all R copies was latency-bound: ~20 us at R = 64.)
 __global__ void __launch_bounds__(256)
-    counts_fold_kernel(const unsigned long long* __restrict__ rep, int B, int n, long long* __restrict__ counts) {
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned long long s = 0;
+    counts_fold_kernel(const unsigned long long* __restrict__ rep, int R, int B, int n, long long* __restrict__ counts) {
+  __shared__ unsigned long long part[8][32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.y * 32 + lane;
+  unsigned long long s = 0;
+  if (i < n) {
+#pragma unroll 4
+    for (int r = w; r < R; r += 8) s += __ldcg(rep + ((size_t)r * B + b) * n + i);
+  }
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < n) {
 #pragma unroll
-    for (int r = 0; r < kCountReplicas; ++r) s += rep[((size_t)r * B + b) * n + i];
+    for (int k = 1; k < 8; ++k) s += part[k][lane];
     counts[(size_t)b * n + i] = (long long)s;
   }
 }
-int launch_counts_fold(const unsigned long long* replicas, int B, int C, int64_t* counts, cudaStream_t stream) {
-  counts_fold_kernel<<<B, 256, 0, stream>>>(replicas, B, 3 * C, reinterpret_cast<long long*>(counts));
+int launch_counts_fold(const unsigned long long* replicas, int R, int B, int C, int64_t* counts, cudaStream_t stream) {
+  counts_fold_kernel<<<dim3(B, (3 * C + 31) / 32), 256, 0, stream>>>(replicas, R, B, 3 * C,
+                                                                   reinterpret_cast<long long*>(counts));
   ROBSEG_LAUNCH_CHECK();
   return 0;
 }
-static size_t count_replica_bytes(int B, int C) { return (size_t)kCountReplicas * B * 3 * C * sizeof(int64_t); }
+// Zeroing the replicas with a kernel of our own: cudaMemsetAsync may be served by a copy engine, and the hand-over
+// between engines costs far more than the 0.2-2 MB memset itself (ROBSEG_COUNTS_MEMSET=1 restores it for comparison).
+__global__ void __launch_bounds__(256) counts_zero_kernel(uint4* __restrict__ p, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+int launch_counts_zero(unsigned long long* replicas, size_t bytes, cudaStream_t stream) {
+  if (getenv("ROBSEG_COUNTS_MEMSET")) {
+    ROBSEG_CUDA(cudaMemsetAsync(replicas, 0, bytes, stream));
+    return 0;
+  }
+  const size_t n16 = bytes / 16;
+  int grid = (int)((n16 + 255) / 256);
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+  if (grid < 1) grid = 1;
+  counts_zero_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(replicas), n16);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+static size_t count_replica_bytes(int B, int C) { return (size_t)count_replicas(C) * B * 3 * C * sizeof(int64_t); }
 
 // ---- host side -----------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -1411,7 +1452,9 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
   p.inv_hw = (float)(1.0 / (double)HW);
   if (counts != nullptr) {
     p.counts = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + loss_partial_bytes(B, HW));
-    ROBSEG_CUDA(cudaMemsetAsync(p.counts, 0, count_replica_bytes(B, C), stream));
+    p.n_rep = count_replicas(C);
+    const int zrc = launch_counts_zero(p.counts, count_replica_bytes(B, C), stream);
+    if (zrc != 0) return zrc;
   }
 
   const int esize = dtype == ROBSEG_F32 ? 4 : 2;
@@ -1440,7 +1483,7 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
   }
   if (rc != 0) return rc;
   if (counts != nullptr) {
-    rc = launch_counts_fold(p.counts, B, C, counts, stream);
+    rc = launch_counts_fold(p.counts, p.n_rep, B, C, counts, stream);
     if (rc != 0) return rc;
   }
   if (loss_img || track_img || correct_img || valid_img) {

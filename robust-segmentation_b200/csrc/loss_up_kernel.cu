@@ -41,8 +41,8 @@ struct LossUpParams {
   float4* contrib;  // [B][h+1][C][w+1] corner contributions (a,b,c,d), or nullptr (no gradient)
   int64_t* pred;
   float4* partials;
-  unsigned long long* counts;  // [kCountReplicas][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
-  int kind, ignore_index, B, C, h, w, H, W;
+  unsigned long long* counts;  // [n_rep][B][3][C] inter / tgt / prd (zeroed by the launcher), or nullptr
+  int kind, ignore_index, B, C, h, w, H, W, n_rep;
   int groups_x, tiles_per_img, num_tiles;
   float inv_hw;
 };
@@ -75,6 +75,14 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
   float2* buf = reinterpret_cast<float2*>(tab + (size_t)C * NDC);
   const int dc = lane / R;
   const bool argmax_only = p.kind == ROBSEG_LOSS_ARGMAX;
+  // class counters: a tile is counted while the NEXT one is processed, so the global reductions are long complete
+  // at the next warp barrier (issued right before it they cost ~25 % of a launch: the barrier waits for them)
+  int cnt_t[R], cnt_q[R], cnt_b = 0;
+  bool cnt_pending = false;
+  auto count_prev = [&]() {
+    unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (p.n_rep - 1)) * p.B + cnt_b) * 3 * C;
+    count_pixels<R>(cnt, C, cnt_t, cnt_q);
+  };
 
   for (int tile = blockIdx.x * NW + warp; tile < p.num_tiles; tile += gridDim.x * NW) {
     const int b = tile / p.tiles_per_img;
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
                                             : p.ignore_index;
     }
     __syncwarp();
+    if (cnt_pending) count_prev();
     const float4* col = tab + dc;
 
     // ---- pass 1: channel maximum (ARGMAX launches also track the index: strict >, ascending) -------
@@ -331,10 +340,10 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
     }
 
     if (p.counts != nullptr) {  // warp-uniform; pixels outside the image carry y = ignore_index
-      unsigned long long* cnt = p.counts + ((size_t)(blockIdx.x & (kCountReplicas - 1)) * p.B + b) * 3 * C;
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        count_pixel(cnt, C, (y[r] != p.ignore_index) && (y[r] >= 0) && (y[r] < C), y[r], amx[r]);
+        cnt_t[r] = ((y[r] != p.ignore_index) && (y[r] >= 0) && (y[r] < C)) ? y[r] : -1, cnt_q[r] = amx[r];
+      cnt_b = b, cnt_pending = true;
     }
     if (p.pred != nullptr && lane_ok) {
 #pragma unroll
@@ -351,6 +360,7 @@ __global__ void __launch_bounds__(256, 1) loss_up_kernel(const LossUpParams p) {
       p.partials[tile] = make_float4(loss_sum, ce_sum, __int_as_float(n_correct), __int_as_float(n_valid));
     __syncwarp();  // the next tile rewrites tab
   }
+  if (cnt_pending) count_prev();
 }
 
 // dlow[b][c][y][x] = the corner contributions that target this cell, added in a fixed order.
@@ -419,7 +429,7 @@ static int launch_up(LossUpParams p, cudaStream_t stream) {
 
 using namespace robseg;
 
-static size_t up_replica_bytes(int B, int C) { return (size_t)kCountReplicas * B * 3 * C * sizeof(int64_t); }
+static size_t up_replica_bytes(int B, int C) { return (size_t)count_replicas(C) * B * 3 * C * sizeof(int64_t); }
 extern "C" size_t robseg_loss_upsampled_workspace_bytes(int B, int C, int h, int w, int H, int W) {
   if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || H % h != 0) return 0;
   const int R = H / h;
@@ -455,13 +465,15 @@ static int loss_upsampled_impl(const float* low, const int64_t* labels, const fl
   if (counts != nullptr) {
     p.counts = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + partial_bytes(B, h, W, R) +
                                                      contrib_bytes(B, C, h, w));
-    ROBSEG_CUDA(cudaMemsetAsync(p.counts, 0, up_replica_bytes(B, C), stream));
+    p.n_rep = count_replicas(C);
+    const int zrc = launch_counts_zero(p.counts, up_replica_bytes(B, C), stream);
+    if (zrc != 0) return zrc;
   }
   int rc = R == 16 ? launch_up<16>(p, stream) : R == 8 ? launch_up<8>(p, stream)
            : R == 4 ? launch_up<4>(p, stream) : launch_up<2>(p, stream);
   if (rc != 0) return rc;
   if (counts != nullptr) {
-    rc = launch_counts_fold(p.counts, B, C, counts, stream);
+    rc = launch_counts_fold(p.counts, p.n_rep, B, C, counts, stream);
     if (rc != 0) return rc;
   }
   if (want_grad) {

@@ -90,6 +90,68 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Forward for any up-sampling ratio whose rows cannot be stored as aligned vectors (W % 4 != 0: the reference's
+// 119 -> 473 PASCAL-VOC logits).  The quad kernel above then writes four 4-byte stores per thread at a 16-byte lane
+// stride -- every store instruction touches 16 sectors partially -- and ran at 35 % of the roofline.  Here a lane owns
+// ONE output column and a block a strip of 32 output rows: every store instruction of a warp is 128 contiguous bytes
+// and the x-taps are per-lane constants.  A thread keeps the two x-interpolated input rows its current output row
+// reads (top, bot) in registers plus the NEXT input row, prefetched: with a ratio >= 1 the walk crosses at most one
+// input row per output row, so a per-strip table holds (w0, w1, advance?) per row and an advance is top <- bot <- next
+// plus one new 2-load prefetch, consumed ~ratio rows later.  ATen's operation order:
+// w0y * (w0x*a + w1x*b) + w1y * (w0x*c + w1x*d).  (Measured alternatives, all slower: re-loading on demand -- stalls on
+// the loads; staging all input rows of the strip in shared memory, per row or per interval -- 20-25 instructions per
+// output; profiles/r02_upsample_walk_forward.md.)
+constexpr int kWalkStrip = 32;
+__global__ void __launch_bounds__(128)
+    upsample_fwd_walk_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h, int w,
+                             int H, int W, float sy, float sx) {
+  __shared__ float4 ytab[kWalkStrip];  // (w0, w1, advance as int bits, -) per output row of the strip
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y0 = blockIdx.y * kWalkStrip, rows = min(kWalkStrip, H - Y0);
+  if (threadIdx.x < rows) {
+    const int r = threadIdx.x;
+    const Tap t = make_tap(Y0 + r, sy, h), tp = make_tap(Y0 + max(r - 1, 0), sy, h);
+    ytab[r] = make_float4(t.w0, t.w1, __int_as_float(r > 0 && t.i0 != tp.i0 ? 1 : 0), 0.f);
+  }
+  __syncthreads();
+  if (X >= W) return;
+  const Tap tx = make_tap(X, sx, w), t0 = make_tap(Y0, sy, h);
+  const int off0 = t0.i0 * w + tx.i0, off1 = t0.i0 * w + tx.i1;  // element offsets inside a plane (< 2^31)
+  const int d1 = (t0.i1 - t0.i0) * w;                            // 0 at the bottom border
+  for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float* base = in + p * (int64_t)h * w;
+    int nrow = min(t0.i1 + 1, h - 1);  // the row after (i0, i1)
+    float top = tx.w0 * __ldg(base + off0) + tx.w1 * __ldg(base + off1);
+    float bot = tx.w0 * __ldg(base + off0 + d1) + tx.w1 * __ldg(base + off1 + d1);
+    float nxt = tx.w0 * __ldg(base + nrow * w + tx.i0) + tx.w1 * __ldg(base + nrow * w + tx.i1);
+    float* o = out + (p * H + Y0) * (int64_t)W + X;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r, o += W) {
+      const float4 t = ytab[r];
+      if (__float_as_int(t.z)) {  // warp-uniform: all lanes walk the same rows
+        top = bot, bot = nxt;
+        nrow = min(nrow + 1, h - 1);
+        nxt = tx.w0 * __ldg(base + nrow * w + tx.i0) + tx.w1 * __ldg(base + nrow * w + tx.i1);
+      }
+      __stcs(o, t.x * top + t.y * bot);
+    }
+  }
+}
+
+static int launch_fwd_walk(const float* in, float* out, int64_t planes, int h, int w, int H, int W, float sy,
+                           float sx, cudaStream_t stream) {
+  int bs = 128;  // the block width that wastes the fewest lanes on the last block of a row
+  for (int cand : {96, 64})
+    if ((W + cand - 1) / cand * cand < (W + bs - 1) / bs * bs) bs = cand;
+  const int gx = (W + bs - 1) / bs, gy = (H + kWalkStrip - 1) / kWalkStrip;
+  int64_t gz = ((int64_t)sm_count() * 16 * (128 / bs) + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
+  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
+  if (gz > 65535) gz = 65535;
+  upsample_fwd_walk_kernel<<<dim3(gx, gy, (unsigned)gz), bs, 0, stream>>>(in, out, planes, h, w, H, W, sy, sx);
+  ROBSEG_LAUNCH_CHECK();
+  return 0;
+}
+
 // Deterministic gather backward.  Block = 256 threads, tile TY x TX input cells; the block
 // builds the per-cell tap tables once (they depend only on the cell), then loops over its
 // planes: stage the output-gradient region in shared memory (each element read once, coalesced),
@@ -698,6 +760,10 @@ extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int
       case 8: return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
       default: break;
     }
+  }
+  if ((W % 4 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0) && H >= h && W >= w && !getenv("ROBSEG_UP_FWD_QUAD")) {
+    // rows that cannot be written as aligned 16-byte vectors: one output column per lane, walking down a strip
+    if ((int64_t)h * w < ((int64_t)1 << 30)) return launch_fwd_walk(in, out, planes, h, w, H, W, sy, sx, stream);
   }
   const int64_t quads = (int64_t)H * ((W + 3) / 4);
   ROBSEG_REQUIRE(quads < ((int64_t)1 << 30), "plane too large");
