@@ -95,45 +95,53 @@ __global__ void __launch_bounds__(128)
 // stride -- every store instruction touches 16 sectors partially -- and ran at 35 % of the roofline.  Here a lane owns
 // ONE output column and a block a strip of 32 output rows: every store instruction of a warp is 128 contiguous bytes
 // and the x-taps are per-lane constants.  A thread keeps the two x-interpolated input rows its current output row
-// reads (top, bot) in registers plus the NEXT input row, prefetched: with a ratio >= 1 the walk crosses at most one
-// input row per output row, so a per-strip table holds (w0, w1, advance?) per row and an advance is top <- bot <- next
-// plus one new 2-load prefetch, consumed ~ratio rows later.  ATen's operation order:
-// w0y * (w0x*a + w1x*b) + w1y * (w0x*c + w1x*d).  (Measured alternatives, all slower: re-loading on demand -- stalls on
-// the loads; staging all input rows of the strip in shared memory, per row or per interval -- 20-25 instructions per
-// output; profiles/r02_upsample_walk_forward.md.)
+// reads (top, bot) in registers and re-loads only when the walk crosses an input row (every ~ratio rows; the row that
+// was "bottom" becomes "top").  Row taps come from a per-strip shared-memory table (one broadcast LDS.128 per row).
+// ATen's operation order: w0y * (w0x*a + w1x*b) + w1y * (w0x*c + w1x*d).
+// Three restructurings were measured and were slower (profiles/r02_upsample_walk_forward.md): staging every input row
+// of the strip in shared memory (per-row or per-interval tables: 20-25 instructions per output) and prefetching the
+// next input row into a third register.
 constexpr int kWalkStrip = 32;
 __global__ void __launch_bounds__(128)
     upsample_fwd_walk_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int h, int w,
                              int H, int W, float sy, float sx) {
-  __shared__ float4 ytab[kWalkStrip];  // (w0, w1, advance as int bits, -) per output row of the strip
+  __shared__ float4 ytab[kWalkStrip];  // (i0, i1 as int bits, w0, w1) per output row of the strip
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y0 = blockIdx.y * kWalkStrip, rows = min(kWalkStrip, H - Y0);
   if (threadIdx.x < rows) {
-    const int r = threadIdx.x;
-    const Tap t = make_tap(Y0 + r, sy, h), tp = make_tap(Y0 + max(r - 1, 0), sy, h);
-    ytab[r] = make_float4(t.w0, t.w1, __int_as_float(r > 0 && t.i0 != tp.i0 ? 1 : 0), 0.f);
+    const Tap t = make_tap(Y0 + threadIdx.x, sy, h);
+    ytab[threadIdx.x] = make_float4(__int_as_float(t.i0), __int_as_float(t.i1), t.w0, t.w1);
   }
   __syncthreads();
   if (X >= W) return;
-  const Tap tx = make_tap(X, sx, w), t0 = make_tap(Y0, sy, h);
-  const int off0 = t0.i0 * w + tx.i0, off1 = t0.i0 * w + tx.i1;  // element offsets inside a plane (< 2^31)
-  const int d1 = (t0.i1 - t0.i0) * w;                            // 0 at the bottom border
+  const Tap tx = make_tap(X, sx, w);
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
     const float* base = in + p * (int64_t)h * w;
-    int nrow = min(t0.i1 + 1, h - 1);  // the row after (i0, i1)
-    float top = tx.w0 * __ldg(base + off0) + tx.w1 * __ldg(base + off1);
-    float bot = tx.w0 * __ldg(base + off0 + d1) + tx.w1 * __ldg(base + off1 + d1);
-    float nxt = tx.w0 * __ldg(base + nrow * w + tx.i0) + tx.w1 * __ldg(base + nrow * w + tx.i1);
     float* o = out + (p * H + Y0) * (int64_t)W + X;
-#pragma unroll 4
+    int cur0 = -1, cur1 = -1;
+    float top = 0.f, bot = 0.f;
     for (int r = 0; r < rows; ++r, o += W) {
       const float4 t = ytab[r];
-      if (__float_as_int(t.z)) {  // warp-uniform: all lanes walk the same rows
-        top = bot, bot = nxt;
-        nrow = min(nrow + 1, h - 1);
-        nxt = tx.w0 * __ldg(base + nrow * w + tx.i0) + tx.w1 * __ldg(base + nrow * w + tx.i1);
+      const int i0 = __float_as_int(t.x), i1 = __float_as_int(t.y);
+      if (i0 != cur0) {  // warp-uniform: all lanes walk the same rows
+        if (i0 == cur1) {
+          top = bot;
+        } else {
+          const float* rp = base + (int64_t)i0 * w;
+          top = tx.w0 * __ldg(rp + tx.i0) + tx.w1 * __ldg(rp + tx.i1);
+        }
+        cur0 = i0;
       }
-      __stcs(o, t.x * top + t.y * bot);
+      if (i1 != cur1) {
+        if (i1 == i0) {
+          bot = top;
+        } else {
+          const float* rp = base + (int64_t)i1 * w;
+          bot = tx.w0 * __ldg(rp + tx.i0) + tx.w1 * __ldg(rp + tx.i1);
+        }
+        cur1 = i1;
+      }
+      __stcs(o, t.z * top + t.w * bot);
     }
   }
 }
