@@ -130,9 +130,28 @@ __device__ __forceinline__ void count_keys(unsigned long long* arr, bool valid, 
   if ((left >> lane) & 1u) atomicAdd(arr + key, 1ull);
 }
 __device__ __forceinline__ void count_pixel(unsigned long long* cnt, int C, bool valid, int t, int q) {
-  count_keys(cnt + C, valid, t);              // target
-  count_keys(cnt + 2 * C, valid, q);          // prediction (only where the label is valid)
-  count_keys(cnt, valid && t == q, t);        // intersection
+  // target and intersection share the label as their key: one extraction serves both arrays
+  const int lane = threadIdx.x & 31;
+  unsigned left = __ballot_sync(0xffffffffu, valid);
+  const unsigned hits = __ballot_sync(0xffffffffu, valid && t == q);
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (left == 0u) break;  // warp-uniform
+    const int first = __ffs(left) - 1;
+    const int k0 = __shfl_sync(0xffffffffu, t, first);
+    const unsigned same = __ballot_sync(0xffffffffu, valid && t == k0) & left;
+    if (lane == first) {
+      atomicAdd(cnt + C + k0, (unsigned long long)__popc(same));
+      const int h = __popc(same & hits);
+      if (h) atomicAdd(cnt + k0, (unsigned long long)h);
+    }
+    left &= ~same;
+  }
+  if ((left >> lane) & 1u) {
+    atomicAdd(cnt + C + t, 1ull);
+    if (t == q) atomicAdd(cnt + t, 1ull);
+  }
+  count_keys(cnt + 2 * C, valid, q);  // prediction (only where the label is valid)
 }
 // All N pixels of every lane at once (t[j] < 0: pixel not counted).  Fast path for the common case on real label
 // maps -- the whole warp tile lies inside one region, i.e. every (label, prediction) pair is the same: one compare

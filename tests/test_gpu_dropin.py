@@ -173,6 +173,72 @@ def test_config1_reference_attacker_same_gpu_vs_dropin(env, loss):
     _ = P
 
 
+@pytest.mark.parametrize("loss", ["mask-ce-bal", "js-avg"])
+def test_config3_reference_segmenter_fused_loss_vs_reference_attacker(env, loss):
+    """BASELINE configs[2]'s consumer as the reference builds it (SegMenter over VisionTransformer ViT-S/16 + a 2-layer
+    MaskTransformer, semseg/models/segmenter.py:193-231; materialised-softmax attention and all), random init, at
+    128 x 128 so the test stays small.  The reference's attacker runs as-is on it on this GPU; the drop-in runs on the
+    SAME module after ``dropin.accelerate`` -- the class masks are handed over BEFORE the x16 bilinear up-sampling
+    (``forward_lowres``) and the loss kernel interpolates on the fly (robseg_loss_upsampled_fwd_bwd_counts).  Same
+    random start -> identical first model input; first update per BASELINE.json's rule (differences only where the
+    reference's |grad| is below 1e-5 of the image's maximum); accuracies of the returned points close; the class
+    counters the attack returns equal robseg_pixel_hist on a re-forward of its adversarial point."""
+    env.dropin.uninstall()
+    import semseg.attacker as RA
+    from importlib import import_module
+
+    assert not RA.__name__.startswith("robseg_b200")
+    S, C, B = 128, 19, 2
+    torch.manual_seed(0)
+    model = env.dropin.reference_model("segmenter", "S", C, S).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(B, 3, S, S, generator=g).cuda()
+    with torch.no_grad():
+        y = model(x).argmax(1)  # labels = clean predictions: the attack has something to flip
+    y[0, :3] = -1
+    w = (0.5 + torch.rand(C, generator=g))
+    kw = dict(norm="Linf", eps=8 / 255.0, n_iter=10, loss=loss, track_loss="ce-avg", use_rs=True, early_stop=True,
+              num_classes=C)
+    rr = _Rec(model).eval()
+    with cfg1.seeded_rand_like(11):
+        xr, lr, ar = RA.apgd_largereps(rr, x.clone(), y, w, **kw)
+    att = env.dropin.install(REF)
+    ops = import_module("robseg_b200.ops")
+    try:
+        env.dropin.accelerate(model)  # fuses the x16 up-sampling into the loss for SegMenter
+        assert hasattr(model, "forward_lowres")
+        low = model.forward_lowres(x)
+        assert low.shape[-1] == S // 16 and ops.can_fuse_upsample(low, y)
+        ro = _Rec(model).eval()
+        ro.forward_lowres = lambda t: (ro.inputs.append(t.detach().clone()), model.forward_lowres(t))[1]
+        n0 = env.lib.launches
+        with cfg1.seeded_rand_like(11):
+            xo, lo, ao, cnt = att.apgd_largereps(ro, x.clone(), y, w, return_counts=True, **kw)
+        assert env.lib.launches > n0
+    finally:
+        env.dropin.uninstall()
+    assert torch.equal(rr.inputs[0], ro.inputs[0])
+    x0 = rr.inputs[0].clone().requires_grad_()
+    lp = RA.criterion_dict[loss](model(x0), y, w)
+    (g0,) = torch.autograd.grad(RA.pixel_to_img_loss(lp, 1 - (y == -1).float()).sum(), [x0])
+    mism = rr.inputs[1] != ro.inputs[1]
+    gmax = g0.abs().flatten(1).amax(1).view(-1, 1, 1, 1)
+    # the fused kernel interpolates with 3 FMAs, ATen with a 4-term sum: logits agree to ~1 ulp, so the rule's
+    # tolerance applies to the gradient itself
+    assert bool((g0.abs()[mism] <= (1e-5 * gmax).expand_as(g0)[mism]).all()), \
+        "first update differs at an element whose |grad| is above the tolerance"
+    assert float(mism.float().mean()) <= 1e-3
+    assert float((xo - x).abs().max()) <= 8 / 255.0 + 1e-6
+    assert float((ar - ao).abs().max()) <= 0.05, (ar, ao)
+    with torch.no_grad():
+        again = model(xo).argmax(1)
+    hist = ops.pixel_hist(again, y, C)
+    tot = int(hist["tgt"].sum())
+    for k, name in enumerate(("inter", "tgt", "prd")):  # re-forward vs in-attack argmax: equal up to near-ties
+        assert int((cnt[:, k] - hist[name]).abs().sum()) <= max(2, tot // 500), name
+    assert torch.equal(cnt[:, 1], hist["tgt"])
+
+
 def test_run_infer_main_executes_the_reference_main_block(env, tmp_path):
     """dropin.run_infer_main: the reference's ``tools/infer.py`` __main__ block (:220-413), compiled from
     the checkout's own file, with a synthetic dataset and a seed-0 checkpoint on disk."""
