@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "robust-segmentation_b200", "librobseg_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()  # noqa: E731
-WATCH = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "MUFU.EX2", "MUFU.LG2", "FMNMX3", "HMNMX2", "STG.E.EF", "STG.E",
-         "LDS.128", "LDS.64", "ATOMS", "RED.E", "SHFL", "MATCH", "UTC", "HMMA", "LDTM"]
+WATCH = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "MUFU.EX2", "MUFU.LG2", "FMNMX3", "HMNMX2", "HMUL2", "STG.E.EF", "STG.E",
+         "LDS.128", "LDS.64", "ATOMS", "REDG", "RED.E", "SHFL", "MATCH", "UTC", "HMMA", "LDTM"]
 counts, order, total = collections.defaultdict(collections.Counter), [], collections.Counter()
 fn = None
 for line in sass.splitlines():
@@ -31,7 +31,7 @@ for line in sass.splitlines():
 print("# SASS census of librobseg_b200.so (sm_100a), `cuobjdump -sass`, round 2\n")
 print("Static instruction counts per kernel for the mnemonics that identify the design: `UTMALDG` = TMA tensor load "
       "(`cp.async.bulk.tensor`), `SYNCS` = mbarrier, `LDGSTS` = `cp.async`, `MUFU.EX2` = `ex2.approx`, `FMNMX3` = 3-input max, "
-      "`STG.E.EF` = streaming (`st.global.cs`) stores, `ATOMS`/`RED` = shared / global atomics.  No `UTMASTG`: the gradient is "
+      "`STG.E.EF` = streaming (`st.global.cs`) stores, `HMUL2` / `HMNMX2` = the packed bf16 multiply / max of the bf16 loss kernel, `ATOMS` = shared-memory atomics, `REDG` = global reductions without return value (the per-image class counters of the loss kernels).  No `UTMASTG`: the gradient is "
       "written from registers with `st.global.cs` (one 8-16 B store per lane and channel: already full coalesced lines, a TMA "
       "store would need the gradient staged in shared memory the kernel has no room for).  No tensor-core instructions "
       "(`UTC*MMA`, `HMMA`) anywhere: the path has no dense contraction.\n")
