@@ -211,12 +211,19 @@ __device__ __forceinline__ void tile_labels(const LossParams& p, int tile_idx, i
 // sits at column phase(c) + i, phase(c) = (ph0 + c * (HW & 3)) & 3.  Rows c, c+4, c+8, ... share their phase,
 // so the unrolled loops (which start at multiples of 4) use four precomputed offsets; shared memory is read
 // with conflict-free scalar loads (lane + 32 j).
-template <typename T, int VEC, int G, bool PARTIAL, bool STR = false, bool OVF = false>
+//
+// CREG > 0 (small class counts, C <= CREG; fp32, one warp per stage): the lane's C x VEC logits are read from the
+// stage ONCE into registers and all three passes run on registers with fully unrolled channel loops (padding
+// channels hold -inf: they lose every max, add exp(-inf) = 0 and never equal the maximum).  At C = 21 the
+// shared-memory version issues ~38 instructions per logit -- per-pass row reads, loop and phase arithmetic, tails
+// of the unrolled trips -- and is issue-bound at 72 % (473^2) / 85 % (472^2) of the roofline.
+template <typename T, int VEC, int G, bool PARTIAL, bool STR = false, bool OVF = false, int CREG = 0>
 __device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int tile_idx, int lane, int half,
                                              const PairXch& xch, const int (&y)[VEC], TileCls<VEC>* cls = nullptr,
                                              int ph0 = 0) {
   static_assert(!STR || G == 1, "strided pixels: one warp per stage");
   static_assert(!OVF || (STR && sizeof(T) == 4), "over-fetched rows: fp32, strided pixel ownership");
+  static_assert(CREG == 0 || (G == 1 && sizeof(T) == 4), "register-resident logits: fp32, one warp per stage");
   constexpr int ROW = 32 * VEC;
   constexpr int RS = OVF ? ROW + 4 : ROW;  // row stride of the stage in elements
   constexpr int PS = STR ? 32 : 1;  // distance between the lane's pixels
@@ -276,7 +283,39 @@ __device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int t
   // loss launches find the first maximal channel by equality during pass 2.
   float mx[VEC];
   int amx[VEC];
-  if (argmax_only) {
+  float zr[CREG > 0 ? CREG : 1][VEC];  // CREG: the lane's logits, -inf beyond C
+  if constexpr (CREG > 0) {
+#pragma unroll
+    for (int c = 0; c < CREG; ++c) {
+      if (c < C) {
+        ldrow(c, c, zr[c]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) zr[c][j] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) mx[j] = zr[0][j], amx[j] = argmax_only ? 0 : kNone;
+    if (argmax_only) {
+#pragma unroll
+      for (int c = 1; c < CREG; ++c)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const bool g = zr[c][j] > mx[j];  // ascending, strict: ties keep the lowest channel
+          mx[j] = g ? zr[c][j] : mx[j];
+          amx[j] = g ? c : amx[j];
+        }
+    } else {
+#pragma unroll
+      for (int c = 1; c + 1 < CREG; c += 2)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) mx[j] = fmax3(mx[j], zr[c][j], zr[c + 1][j]);
+      if constexpr (CREG % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) mx[j] = fmaxf(mx[j], zr[CREG - 1][j]);
+      }
+    }
+  } else if (argmax_only) {
     float m[NACC][VEC];
     int am[NACC][VEC];
 #pragma unroll
@@ -487,6 +526,16 @@ __device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int t
       }
     };
     int c = c_hi;
+    if constexpr (CREG > 0) {
+#pragma unroll
+      for (int cc = CREG - 1; cc >= 0; --cc)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          s[cc % NACC][j] += ex2_approx(fmaf(zr[cc][j], kLog2e, -mL[j]));
+          if (zr[cc][j] == mx[j]) amx[j] = cc;  // walking downwards: the last hit is the lowest channel
+        }
+      c = c_lo;  // the shared-memory loops below have nothing left to do
+    }
     // one half trip of 4 rows (rows c-1 .. c-4), walking downwards like the full trips
     auto half_trip = [&]() {
 #pragma unroll
@@ -685,6 +734,18 @@ __device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int t
         }
       } else {
         c = c_lo;
+        if constexpr (CREG > 0) {
+#pragma unroll
+          for (int cc = 0; cc < CREG; ++cc)
+            if (cc < C) {
+              float g[VEC];
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) g[j] = ex2_approx(fmaf(zr[cc][j], kLog2e, -mL[j])) * kfac[j];
+              stgv(gp, g);
+              gp += hw;
+            }
+          c = c_hi;  // nothing left for the shared-memory loops
+        }
 #pragma unroll 1
         for (; c + UNR <= c_hi; c += UNR) {
           float v[UNR][VEC];
@@ -768,7 +829,7 @@ __device__ __forceinline__ void process_tile(const LossParams& p, T* tile, int t
 // stages; ring item `it` goes to group it % W, slot (it / W) % K.  A stage is only ever
 // consumed by one group, so its mbarrier phases are observed in order (a parity wait is
 // ambiguous for a waiter that is two phases away).
-template <typename T, int VEC, int G>
+template <typename T, int VEC, int G, int CREG = 0>
 __global__ void __launch_bounds__(G == 2 ? 1024 : 512, 1)
     loss_tma_kernel(const __grid_constant__ CUtensorMap tmap, const LossParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -832,9 +893,9 @@ __global__ void __launch_bounds__(G == 2 ? 1024 : 512, 1)
       T* st = reinterpret_cast<T*>(smem + (size_t)s * stage_bytes);
       TileCls<VEC>* out = counting ? &now : nullptr;
       if (partial)
-        process_tile<T, VEC, G, true>(p, st, tile, lane, half, xch, y, out);
+        process_tile<T, VEC, G, true, false, false, CREG>(p, st, tile, lane, half, xch, y, out);
       else
-        process_tile<T, VEC, G, false>(p, st, tile, lane, half, xch, y, out);
+        process_tile<T, VEC, G, false, false, false, CREG>(p, st, tile, lane, half, xch, y, out);
       if (counting) prev = now;
       pending = counting;
       if constexpr (sizeof(T) == 2)  // bf16 writes e into the stage: order those generic-proxy stores before the
@@ -1005,7 +1066,7 @@ __global__ void __launch_bounds__(256) loss_generic_strided_kernel(const LossPar
 // instruction is full.  The consumer side (process_tile<..., STR, OVF>) reads pixel i of row c at column
 // phase(c) + i.  Chunks beyond the tensor are zero-filled (src-size < 16); up to 3 floats of over-fetch per row
 // come from the neighbouring rows' bytes of the same tensor, i.e. from L2.
-template <int VEC>
+template <int VEC, int CREG = 0>
 __global__ void __launch_bounds__(256) loss_generic_ovf_kernel(const LossParams p, const int K, const int64_t n_total) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int ROW = 32 * VEC, RS = ROW + 4, NCH = ROW / 4 + 1;
@@ -1084,8 +1145,8 @@ __global__ void __launch_bounds__(256) loss_generic_ovf_kernel(const LossParams 
     const int ph0 = (int)(row0(tile) & 3);
     if (pending) count_tile<VEC>(p, prev);  // one tile late: see TileCls
     TileCls<VEC>* out = p.counts != nullptr ? &now : nullptr;
-    if (full) process_tile<float, VEC, 1, false, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
-    else process_tile<float, VEC, 1, true, true, true>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
+    if (full) process_tile<float, VEC, 1, false, true, true, CREG>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
+    else process_tile<float, VEC, 1, true, true, true, CREG>(p, cur, tile, lane, 0, PairXch{}, y, out, ph0);
     if (out != nullptr) prev = now, pending = true;
     __syncwarp();
   }
@@ -1213,6 +1274,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// Small class counts (VOC 21, Cityscapes 19): logits kept in registers (process_tile CREG), 2 pixels per lane.
+// ROBSEG_LOSS_CREG=0 restores the shared-memory passes.
+constexpr int kRegChannels = 24;
+static bool creg_enabled() {
+  const char* e = getenv("ROBSEG_LOSS_CREG");
+  return !(e && atoi(e) == 0);
+}
+
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // ring + barriers + alignment slack
 constexpr size_t kMaxDynSmem = 227 * 1024;         // opt-in dynamic shared memory per CTA on sm_100
 
@@ -1234,7 +1303,7 @@ static int pick_vec(int C, int esize, bool with_grad) {
   return vec;
 }
 
-template <typename T, int VEC, int G>
+template <typename T, int VEC, int G, int CREG = 0>
 static int launch_tma(const LossParams& p0, cudaStream_t stream) {
   LossParams p = p0;
   constexpr int ROW = 32 * VEC;
@@ -1273,7 +1342,7 @@ static int launch_tma(const LossParams& p0, cudaStream_t stream) {
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ROBSEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
 
-  auto kern = loss_tma_kernel<T, VEC, G>;
+  auto kern = loss_tma_kernel<T, VEC, G, CREG>;
   ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count();
   const int max_useful = (p.num_tiles + W - 1) / W;
@@ -1329,6 +1398,7 @@ static int launch_generic(const LossParams& p0, cudaStream_t stream, int* tiles_
         const int ctas_sm = warps_sm / W;
         const size_t smem = (size_t)W * K * st;
         auto kern = vec == 4 ? loss_generic_ovf_kernel<4> : vec == 2 ? loss_generic_ovf_kernel<2> : loss_generic_ovf_kernel<1>;
+        if (vec == 2 && p.C <= kRegChannels && creg_enabled()) kern = loss_generic_ovf_kernel<2, kRegChannels>;
         ROBSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         p.tiles_per_img = *tiles_per_img = (int)((p.HW + 32 * vec - 1) / (32 * vec));
         p.num_tiles = p.B * p.tiles_per_img;
@@ -1468,7 +1538,13 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
     // (argmax-only launches are pure streaming reads: wide rows again)
     const int vec = pick_vec(C, esize, dlogits != nullptr || loss_kind == ROBSEG_LOSS_ARGMAX);
     tiles_per_img = (int)((HW + 32 * vec - 1) / (32 * vec));
-    if (dtype == ROBSEG_F32) {
+    // (gradient launches only: loss-only / argmax launches are read-only streams that do better with the wide
+    // 512-byte rows pick_vec gives them -- measured at 24x21x472^2: 0.120 vs 0.146 ms)
+    if (dtype == ROBSEG_F32 && C <= kRegChannels && dlogits != nullptr && creg_enabled() && !getenv("ROBSEG_LOSS_VEC") &&
+        !getenv("ROBSEG_LOSS_G")) {
+      tiles_per_img = (int)((HW + 63) / 64);
+      rc = launch_tma<float, 2, 1, kRegChannels>(p, stream);
+    } else if (dtype == ROBSEG_F32) {
       rc = vec == 4 ? launch_tma_pick<float, 4>(p, stream)
                     : vec == 2 ? launch_tma_pick<float, 2>(p, stream)
                                : launch_tma_pick<float, 1>(p, stream);
