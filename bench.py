@@ -525,14 +525,26 @@ def sea_roofline(by, B, C, S, peaks, clocks):
     up-sampling fused into the loss (SegMenter default, --fuse-loss) the [B,C,H,W] tensors never exist: that kernel moves
     1/R^2 of the bytes and is bound by the ex2 pipe (2 ex2 per up-sampled logit, 16 lanes / clk / SM), so its HBM
     fraction is small BY DESIGN; the ex2-pipe fraction is reported beside it."""
-    if "loss_grad" in by:
-        lg = by["loss_grad"]
+    if "loss_grad" in by or "loss_grad_counts" in by:
+        lg = by.get("loss_grad") or by["loss_grad_counts"]
         achieved = lg[0] / (lg[1] / 1e3) / 1e9
-        return {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
+        roof = {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
                 "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s", "frac": round(achieved / peaks[0], 4),
                 "traffic": load_traffic("sea_c%d" % C), "peak_source": peaks[1], "launches_timed": lg[2],
                 "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4), "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)}
-    lg = by.get("loss_up_grad", [0, 1e-9, 1])
+        if "loss_grad" in by and "loss_grad_counts" in by:
+            # the last stage's launches also take the per-image class counters; their event bracket holds the zeroing
+            # and fold kernels of the counter replicas next to the loss kernel, so they are reported beside it
+            lc = by["loss_grad_counts"]
+            ac = lc[0] / (lc[1] / 1e3) / 1e9
+            roof["with_class_counters"] = {"launches_timed": lc[2], "avg_bracket_ms": round(lc[1] / max(lc[2], 1), 4),
+                                           "achieved": round(ac, 1), "frac": round(ac / peaks[0], 4),
+                                           "bracket": "counts_zero_kernel + loss_tma_kernel + counts_fold_kernel + loss_finalize_kernel"}
+            tot = lg[0] + lc[0]
+            roof["all_loss_grad_launches"] = {"launches_timed": lg[2] + lc[2],
+                                              "frac": round(tot / ((lg[1] + lc[1]) / 1e3) / 1e9 / peaks[0], 4)}
+        return roof
+    lg = by.get("loss_up_grad") or by.get("loss_up_grad_counts") or [0, 1e-9, 1]
     achieved = lg[0] / (lg[1] / 1e3) / 1e9
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
     ex2_peak = 16 * 148 * mhz * 1e6  # MUFU.EX2 lanes per second (B300_MICROARCH: 16 / clk / SM)
