@@ -426,6 +426,7 @@ def run_ours(args):
     mods["ops"].profile_start()
     ms, keep = timed(args.steps, e2e=False)
     prof = mods["ops"].profile_stop()
+    prof_k = mods["ops"].profile_kernels()
     launches = mods["lib"].launches - launches0
     ms_e2e, keep_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
@@ -447,6 +448,12 @@ def run_ours(args):
     by = {}
     for name, nbytes, t in prof:
         d = by.setdefault(name, [0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += t
+        d[2] += 1
+    byk = {}  # the library's own brackets around the main kernel of every loss call (robseg_profile_next_kernel)
+    for name, nbytes, t in prof_k:
+        d = byk.setdefault(name, [0, 0.0, 0])
         d[0] += nbytes
         d[1] += t
         d[2] += 1
@@ -496,7 +503,7 @@ def run_ours(args):
         "e2e": {"value": round(value_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches,
-        "roofline": sea_roofline(by, B, C, S, peaks, clocks),
+        "roofline": sea_roofline(by, byk, B, C, S, peaks, clocks),
     }
     if world == 1 and args.model == "upernet" and not args.fuse_loss and not args.graph and upsample_mode(args):
         del model
@@ -519,39 +526,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def sea_roofline(by, B, C, S, peaks, clocks):
+def sea_roofline(by, byk, B, C, S, peaks, clocks):
     """`roofline` of the dominant robseg kernel of a SEA step, from the per-launch CUDA events of the timed region.
-    Default step: loss_tma_kernel (HBM-bound, algorithmic bytes = logits in + gradient out + labels).  With the final
-    up-sampling fused into the loss (SegMenter default, --fuse-loss) the [B,C,H,W] tensors never exist: that kernel moves
-    1/R^2 of the bytes and is bound by the ex2 pipe (2 ex2 per up-sampled logit, 16 lanes / clk / SM), so its HBM
-    fraction is small BY DESIGN; the ex2-pipe fraction is reported beside it."""
+    Default step: loss_tma_kernel (HBM-bound, algorithmic bytes = logits in + gradient out + labels); `achieved` is over
+    the kernel's OWN launch duration -- events the library records immediately before and after that one launch
+    (robseg_profile_next_kernel), every loss+gradient launch of the timed steps, counted or not -- and the wider bracket
+    around the whole C call (+ the per-image finalize kernel, + the counter zeroing / fold kernels of counted launches)
+    is reported beside it.  With the final up-sampling fused into the loss (SegMenter default, --fuse-loss) the
+    [B,C,H,W] tensors never exist: that kernel moves 1/R^2 of the bytes and is bound by the ex2 pipe (2 ex2 per
+    up-sampled logit, 16 lanes / clk / SM), so its HBM fraction is small BY DESIGN; the ex2-pipe fraction is reported
+    beside it."""
+    def agg(d, *names):
+        tot = [0, 0.0, 0]
+        for n in names:
+            v = d.get(n)
+            if v:
+                tot = [tot[0] + v[0], tot[1] + v[1], tot[2] + v[2]]
+        return tot if tot[2] else None
+
+    def rate(v):
+        return v[0] / (v[1] / 1e3) / 1e9
+
     if "loss_grad" in by or "loss_grad_counts" in by:
-        lg = by.get("loss_grad") or by["loss_grad_counts"]
-        achieved = lg[0] / (lg[1] / 1e3) / 1e9
+        call = agg(by, "loss_grad", "loss_grad_counts")
+        kern = agg(byk, "loss_grad", "loss_grad_counts") or call
+        achieved = rate(kern)
+        traffic, capture = load_traffic("sea_c%d" % C)
         roof = {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused loss+dlogits, C=%d)" % C,
                 "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s", "frac": round(achieved / peaks[0], 4),
-                "traffic": load_traffic("sea_c%d" % C), "peak_source": peaks[1], "launches_timed": lg[2],
-                "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4), "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)}
-        if "loss_grad" in by and "loss_grad_counts" in by:
-            # the last stage's launches also take the per-image class counters; their event bracket holds the zeroing
-            # and fold kernels of the counter replicas next to the loss kernel, so they are reported beside it
-            lc = by["loss_grad_counts"]
-            ac = lc[0] / (lc[1] / 1e3) / 1e9
-            roof["with_class_counters"] = {"launches_timed": lc[2], "avg_bracket_ms": round(lc[1] / max(lc[2], 1), 4),
-                                           "achieved": round(ac, 1), "frac": round(ac / peaks[0], 4),
-                                           "bracket": "counts_zero_kernel + loss_tma_kernel + counts_fold_kernel + loss_finalize_kernel"}
-            tot = lg[0] + lc[0]
-            roof["all_loss_grad_launches"] = {"launches_timed": lg[2] + lc[2],
-                                              "frac": round(tot / ((lg[1] + lc[1]) / 1e3) / 1e9 / peaks[0], 4)}
+                "traffic": traffic, "traffic_capture": capture, "peak_source": peaks[1], "launches_timed": kern[2],
+                "avg_launch_ms": round(kern[1] / max(kern[2], 1), 4),
+                "algorithmic_bytes_per_launch": kern[0] // max(kern[2], 1),
+                "timed_with": ("events recorded by the library around the kernel launch itself (robseg_profile_next_kernel)"
+                               if kern is not call else "events around the C call"),
+                "frac_of_spec_8TBps": round(achieved / 8000.0, 4)}
+        # the brackets around the whole C call: + loss_finalize_kernel, and for the last stage's launches (which also
+        # take the per-image class counters) + counts_zero_kernel and counts_fold_kernel
+        for key, names, what in (
+                ("call_bracket", ("loss_grad",), "loss_tma_kernel + loss_finalize_kernel"),
+                ("call_bracket_with_class_counters", ("loss_grad_counts",),
+                 "counts_zero_kernel + loss_tma_kernel + counts_fold_kernel + loss_finalize_kernel")):
+            v = agg(by, *names)
+            if v:
+                roof[key] = {"launches_timed": v[2], "avg_bracket_ms": round(v[1] / v[2], 4),
+                             "achieved": round(rate(v), 1), "frac": round(rate(v) / peaks[0], 4), "bracket": what}
+        for key, names in (("kernel_uncounted", ("loss_grad",)), ("kernel_with_class_counters", ("loss_grad_counts",))):
+            v = agg(byk, *names)
+            if v:
+                roof[key] = {"launches_timed": v[2], "avg_launch_ms": round(v[1] / v[2], 4),
+                             "frac": round(rate(v) / peaks[0], 4)}
         return roof
-    lg = by.get("loss_up_grad") or by.get("loss_up_grad_counts") or [0, 1e-9, 1]
+    lg = (agg(byk, "loss_up_grad", "loss_up_grad_counts") or agg(by, "loss_up_grad", "loss_up_grad_counts")
+          or [0, 1e-9, 1])
     achieved = lg[0] / (lg[1] / 1e3) / 1e9
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
     ex2_peak = 16 * 148 * mhz * 1e6  # MUFU.EX2 lanes per second (B300_MICROARCH: 16 / clk / SM)
     ex2_rate = 2.0 * B * C * S * S * lg[2] / (lg[1] / 1e3)  # pass 2 + pass 3: two ex2 per up-sampled logit
     return {"bound": "hbm", "kernel": "loss_up_kernel<R> (loss taken through the bilinear up-sampling, C=%d)" % C,
             "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s", "frac": round(achieved / peaks[0], 4),
-            "traffic": load_traffic("sea_up_c%d" % C), "peak_source": peaks[1], "launches_timed": lg[2],
+            "traffic": load_traffic("sea_up_c%d" % C)[0], "peak_source": peaks[1], "launches_timed": lg[2],
             "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4), "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1),
             "note": "not HBM-bound by construction (the [B,C,H,W] logits / gradient never exist): limited by the ex2 pipe",
             "ex2_pipe": {"achieved_Gex2_per_s": round(ex2_rate / 1e9, 1), "peak_Gex2_per_s": round(ex2_peak / 1e9, 1),
@@ -572,7 +605,7 @@ def loss_kernel_probe(mods, dev, B, C, S, reps=5):
     y = torch.randint(0, C, (B, S, S), device=dev, generator=g)
     y = torch.where(torch.rand(B, S, S, device=dev, generator=g) < 0.5, z.argmax(1), y)
     dbuf = torch.empty_like(z)
-    ts = []
+    ts, tc = [], []
     for i in range(3 + reps):
         # the wrapper's own events bracket just the C call (kernel + per-image finaliser): outer events would
         # also count the host's argument marshalling while the GPU sits idle
@@ -580,15 +613,19 @@ def loss_kernel_probe(mods, dev, B, C, S, reps=5):
         ops.loss_fwd_bwd(z, y, "mask-ce-avg", None, dlogits_out=dbuf)
         torch.cuda.synchronize()
         t = sum(ms_ for _, _, ms_ in ops.profile_stop())
+        tk = sum(ms_ for _, _, ms_ in ops.profile_kernels())  # the loss kernel's own launch
         if i >= 3:
-            ts.append(t)
+            ts.append(tk or t)
+            tc.append(t)
     ms = statistics.median(ts)
     nbytes = 2 * z.numel() * 4 + 8 * y.numel()
     peak = load_peaks()[0]
     del z, y, dbuf
     torch.cuda.empty_cache()
+    mc = statistics.median(tc)
     return {"shape": [B, C, S, S], "ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1),
-            "frac": round(nbytes / ms / 1e6 / peak, 4), "bytes": nbytes}
+            "frac": round(nbytes / ms / 1e6 / peak, 4), "bytes": nbytes,
+            "call_bracket_ms": round(mc, 4), "call_bracket_frac": round(nbytes / mc / 1e6 / peak, 4)}
 
 
 # ------------------------------------------------------------------------------ PIR-AT (configs[3])
@@ -681,6 +718,7 @@ def run_pirat(args, mods, dev, rank, world, local):
             mods["ops"].profile_start()
             ms, last = timed(attack, args.steps)
             prof = mods["ops"].profile_stop()
+            prof_k = mods["ops"].profile_kernels()
             launches = mods["lib"].launches - launches0
             ms_e2e, _ = timed(attack, args.steps, e2e=True)
             clocks = sampler.stop() if rank == 0 else None
@@ -706,6 +744,12 @@ def run_pirat(args, mods, dev, rank, world, local):
         d[1] += t
         d[2] += 1
     lg = by.get("loss_grad", [0, 1e-9, 1])
+    lk = [0, 0.0, 0]  # the loss kernel's own launches (robseg_profile_next_kernel)
+    for name, nbytes, t in prof_k:
+        if name == "loss_grad":
+            lk = [lk[0] + nbytes, lk[1] + t, lk[2] + 1]
+    if lk[2]:
+        lg = lk
     achieved = lg[0] / (lg[1] / 1e3) / 1e9
     ips = lambda m: round(world * B * args.steps / (m / 1e3), 3)  # noqa: E731
     line = {
@@ -735,7 +779,7 @@ def run_pirat(args, mods, dev, rank, world, local):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "loss_tma_kernel<float,VEC=2,G=1> (fused CE loss+dlogits, C=%d)" % C,
                      "achieved": round(achieved, 1), "peak": peaks[0], "unit": "GB/s",
-                     "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C),
+                     "frac": round(achieved / peaks[0], 4), "traffic": load_traffic("sea_c%d" % C)[0],
                      "peak_source": peaks[1], "launches_timed": lg[2],
                      "avg_launch_ms": round(lg[1] / max(lg[2], 1), 4),
                      "algorithmic_bytes_per_launch": lg[0] // max(lg[2], 1)},
@@ -753,12 +797,35 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_sha():
+    """sha256 over the sources the loss kernels are compiled from (what an ncu traffic capture is valid for)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for rel in ("loss_kernel.cu", "common.cuh"):
+        with open(os.path.join(ROOT, "robust-segmentation_b200", "csrc", rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic(key):
+    """(DRAM bytes per launch from the committed ncu --set full capture, provenance).  DRAM bytes need ncu, so the
+    bench cannot measure them live; the capture records the sha of the kernel sources it was taken on
+    (scripts/update_traffic.py) and a capture of other sources is reported as null, not passed on as current."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(key)
+            d = json.load(f)
     except Exception:
-        return None
+        return None, None
+    v = d.get(key)
+    if v is None:
+        return None, None
+    sha, cur = d.get("_kernel_source_sha"), kernel_source_sha()
+    cap = {"report": d.get("_reports", {}).get(key), "kernel_source_sha": sha, "matches_tree": sha == cur}
+    if sha != cur:
+        cap["stale_value"] = v
+        return None, cap
+    return v, cap
 
 
 # ------------------------------------------------------------------------------ microbench
@@ -828,6 +895,23 @@ def run_micro(args, mods, dev, rank, world):
         ms = statistics.median(ts)
         res[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peaks[0], 4),
                      "bytes": nbytes}
+        if name.startswith(("loss_", "argmax")):
+            # the main kernel alone (events recorded by the library around that one launch, robseg_profile_next_kernel):
+            # the bracket above also holds the finalize kernel and, for counted launches, the counter zeroing / fold
+            tk = []
+            for _ in range(5):
+                if nbytes < 2 * l2_flush.numel():
+                    l2_flush.zero_()
+                torch.cuda._sleep(1_000_000)
+                ops.profile_start()
+                fn()
+                torch.cuda.synchronize()
+                ops.profile_stop()
+                tk.append(sum(t for _, _, t in ops.profile_kernels()))
+            mk = statistics.median(tk)
+            if mk > 0:
+                res[name].update({"kernel_ms": round(mk, 4), "kernel_GBps": round(nbytes / mk / 1e6, 1),
+                                  "kernel_frac": round(nbytes / mk / 1e6 / peaks[0], 4)})
 
     es = z.element_size()
     for kind in LOSSES + ["ce-avg"]:
@@ -972,7 +1056,7 @@ def run_micro(args, mods, dev, rank, world):
                                                       "back-to-back device execution, not host launch latency"},
             "roofline": {"bound": "hbm", "achieved": k.get("GBps_slowest_rank", k["GBps"]), "peak": peaks[0], "unit": "GB/s",
                          "frac": k.get("frac_slowest_rank", k["frac"]),
-                         "traffic": load_traffic("micro_c%d_%s" % (C, args.micro_dtype)), "peak_source": peaks[1]},
+                         "traffic": load_traffic("micro_c%d_%s" % (C, args.micro_dtype))[0], "peak_source": peaks[1]},
         }), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -53,6 +53,16 @@ int robseg_version(void);
 /* Reason of the last non-zero return on this thread ("" if none). */
 const char* robseg_last_error(void);
 
+/*
+ * Measurement hook (bench.py's `roofline`): the NEXT robseg_loss_fwd_bwd* / robseg_loss_upsampled_fwd_bwd*
+ * call on this thread records `start_event` immediately before and `stop_event` immediately after its
+ * main kernel (loss_tma_kernel / loss_generic_* / loss_up_kernel) on the call's stream, leaving the small
+ * counter-zeroing, counter-fold and finalize launches of the same call outside the bracket.  Both are
+ * cudaEvent_t created by the caller with timing enabled; one-shot (cleared by the call that uses them);
+ * pass NULL, NULL to cancel.  No effect on results.
+ */
+int robseg_profile_next_kernel(void* start_event, void* stop_event);
+
 /* Bytes of scratch robseg_loss_fwd_bwd needs for a problem of this shape. */
 size_t robseg_loss_workspace_bytes(int B, int C, int64_t HW, int dtype);
 

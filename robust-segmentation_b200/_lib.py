@@ -27,6 +27,7 @@ class RowJob(C.Structure):
 SIGNATURES = {
     "robseg_version": (_i, []),
     "robseg_last_error": (C.c_char_p, []),
+    "robseg_profile_next_kernel": (_i, [_p, _p]),
     "robseg_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i]),
     "robseg_loss_fwd_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _sz, _p]),

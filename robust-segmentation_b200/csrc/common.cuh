@@ -14,6 +14,9 @@ namespace robseg {
 // ---- error plumbing: nothing throws across the C ABI -------------------------------------
 void set_error(const char* fmt, ...);
 int sm_count();  // cached multiProcessorCount of the current device (148 on B200)
+// one-shot events of robseg_profile_next_kernel (thread-local): take_* returns the event and clears it
+cudaEvent_t take_profile_start();
+cudaEvent_t take_profile_stop();
 
 #define ROBSEG_REQUIRE(cond, ...)          \
   do {                                     \

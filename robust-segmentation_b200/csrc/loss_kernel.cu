@@ -1192,9 +1192,21 @@ __global__ void __launch_bounds__(256)
   double l = 0.0, ce = 0.0;
   int k = 0, v = 0;
   const float4* src = partials + (size_t)b * tiles_per_img;
-  for (int i = t; i < tiles_per_img; i += 256) {
-    const float4 q = src[i];
-    l += (double)q.x, ce += (double)q.y, k += __float_as_int(q.z), v += __float_as_int(q.w);
+  // 8 independent loads in flight per thread (the serial loop paid one L2 round trip per partial: 16 of them at
+  // 512^2); the additions keep the ascending-i order, so the sums are bit-identical to the serial loop's
+  constexpr int U = 8;
+  for (int i0 = t; i0 < tiles_per_img; i0 += 256 * U) {
+    float4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + 256 * u;
+      q[u] = i < tiles_per_img ? __ldcg(src + i) : make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(0));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + 256 * u < tiles_per_img)
+        l += (double)q[u].x, ce += (double)q[u].y, k += __float_as_int(q[u].z), v += __float_as_int(q[u].w);
+    }
   }
   sh_l[t] = l, sh_c[t] = ce, sh_k[t] = k, sh_v[t] = v;
   __syncthreads();
@@ -1504,6 +1516,8 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
                              int32_t* correct_img, int32_t* valid_img, int64_t* counts, void* workspace,
                              size_t workspace_bytes, robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // one-shot measurement events (robseg_profile_next_kernel): consumed by this call whatever its outcome
+  const cudaEvent_t prof_start = take_profile_start(), prof_stop = take_profile_stop();
   ROBSEG_REQUIRE(logits && labels, "logits/labels must not be NULL");
   ROBSEG_REQUIRE(dtype == ROBSEG_F32 || dtype == ROBSEG_BF16, "unsupported dtype %d", dtype);
   ROBSEG_REQUIRE(loss_kind >= ROBSEG_LOSS_CE && loss_kind <= ROBSEG_LOSS_ARGMAX,
@@ -1534,6 +1548,7 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
                       (size_t)C * 32 * esize * (esize == 2 ? 2 : 1) * 2 <= kSmemBudget - 512;
   int rc;
   int tiles_per_img;
+  if (prof_start) cudaEventRecord(prof_start, stream);
   if (tma_ok) {
     // (argmax-only launches are pure streaming reads: wide rows again)
     const int vec = pick_vec(C, esize, dlogits != nullptr || loss_kind == ROBSEG_LOSS_ARGMAX);
@@ -1557,6 +1572,7 @@ static int loss_fwd_bwd_impl(const void* logits, int dtype, const int64_t* label
     rc = dtype == ROBSEG_F32 ? launch_generic<float>(p, stream, &tiles_per_img)
                              : launch_generic<__nv_bfloat16>(p, stream, &tiles_per_img);
   }
+  if (prof_stop) cudaEventRecord(prof_stop, stream);
   if (rc != 0) return rc;
   if (counts != nullptr) {
     rc = launch_counts_fold(p.counts, p.n_rep, B, C, counts, stream);

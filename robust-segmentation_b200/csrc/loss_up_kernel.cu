@@ -443,6 +443,8 @@ static int loss_upsampled_impl(const float* low, const int64_t* labels, const fl
                                int32_t* correct_img, int32_t* valid_img, int64_t* counts, void* workspace,
                                size_t workspace_bytes, robseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // one-shot measurement events (robseg_profile_next_kernel): consumed by this call whatever its outcome
+  const cudaEvent_t prof_start = take_profile_start(), prof_stop = take_profile_stop();
   ROBSEG_REQUIRE(low && labels, "low/labels must not be NULL");
   ROBSEG_REQUIRE(loss_kind >= ROBSEG_LOSS_CE && loss_kind <= ROBSEG_LOSS_ARGMAX, "unknown loss kind %d", loss_kind);
   ROBSEG_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0, "bad shape B=%d C=%d h=%d w=%d", B, C, h, w);
@@ -469,8 +471,10 @@ static int loss_upsampled_impl(const float* low, const int64_t* labels, const fl
     const int zrc = launch_counts_zero(p.counts, up_replica_bytes(B, C), stream);
     if (zrc != 0) return zrc;
   }
+  if (prof_start) cudaEventRecord(prof_start, stream);
   int rc = R == 16 ? launch_up<16>(p, stream) : R == 8 ? launch_up<8>(p, stream)
            : R == 4 ? launch_up<4>(p, stream) : launch_up<2>(p, stream);
+  if (prof_stop) cudaEventRecord(prof_stop, stream);
   if (rc != 0) return rc;
   if (counts != nullptr) {
     rc = launch_counts_fold(p.counts, p.n_rep, B, C, counts, stream);

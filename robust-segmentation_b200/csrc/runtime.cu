@@ -27,7 +27,25 @@ int sm_count() {
   return cached[dev];
 }
 
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+cudaEvent_t take_profile_start() {
+  cudaEvent_t e = g_prof_start;
+  g_prof_start = nullptr;
+  return e;
+}
+cudaEvent_t take_profile_stop() {
+  cudaEvent_t e = g_prof_stop;
+  g_prof_stop = nullptr;
+  return e;
+}
+
 }  // namespace robseg
+
+extern "C" int robseg_profile_next_kernel(void* start_event, void* stop_event) {
+  robseg::g_prof_start = static_cast<cudaEvent_t>(start_event);
+  robseg::g_prof_stop = static_cast<cudaEvent_t>(stop_event);
+  return 0;
+}
 
 extern "C" int robseg_version(void) { return ROBSEG_ABI_VERSION; }
 

@@ -23,35 +23,55 @@ _workspaces = {}
 # wrapper brackets its C call with CUDA events on the launching stream and appends
 # (name, algorithmic_bytes, start_event, end_event) here.
 _prof = None
+_prof_k = []   # kernel-level brackets of the same window (robseg_profile_next_kernel)
+_last_k = []
 
 
 def profile_start():
-    global _prof
-    _prof = []
+    global _prof, _prof_k
+    _prof, _prof_k = [], []
 
 
 def profile_stop():
-    """Returns [(name, bytes, ms)]; call after a device synchronize."""
-    global _prof
+    """Returns [(name, bytes, ms)] -- one event bracket per C call; call after a device synchronize.
+    ``profile_kernels()`` then returns the brackets the library itself recorded around the main kernel of
+    every loss call of the same window (the zeroing / fold / finalize launches of the call left outside)."""
+    global _prof, _prof_k, _last_k
     rec, _prof = _prof or [], None
+    _last_k = [(n, b, s.elapsed_time(e)) for n, b, s, e in _prof_k]
+    _prof_k = []
     return [(n, b, s.elapsed_time(e)) for n, b, s, e in rec]
 
 
+def profile_kernels():
+    return list(_last_k)
+
+
 class _timed:
-    def __init__(self, name, nbytes):
-        self.name, self.nbytes = name, nbytes
+    def __init__(self, name, nbytes, main_kernel=False):
+        self.name, self.nbytes, self.main_kernel = name, nbytes, main_kernel
 
     def __enter__(self):
         self.on = _prof is not None and not torch.cuda.is_current_stream_capturing()
         if self.on:
             self.s = torch.cuda.Event(enable_timing=True)
             self.e = torch.cuda.Event(enable_timing=True)
+            if self.main_kernel:
+                # the library re-records these two around its main kernel; recording them here first creates
+                # the cudaEvent_t handles (torch makes them lazily)
+                self.ks = torch.cuda.Event(enable_timing=True)
+                self.ke = torch.cuda.Event(enable_timing=True)
+                self.ks.record()
+                self.ke.record()
+                _lib.load().robseg_profile_next_kernel(self.ks.cuda_event, self.ke.cuda_event)
             self.s.record()
 
     def __exit__(self, *a):
         if self.on and _prof is not None:
             self.e.record()
             _prof.append((self.name, self.nbytes, self.s, self.e))
+            if self.main_kernel:
+                _prof_k.append((self.name, self.nbytes, self.ks, self.ke))
 
 
 def _ptr(t):
@@ -146,13 +166,13 @@ def loss_fwd_bwd(logits, labels, kind, weights=None, grad_scale=None, upstream=N
     # (a counted launch brackets three more small kernels -- zeroing and folding the counter replicas -- so it is
     # profiled under its own name: bench.py's roofline is the loss kernel's own launch duration)
     tag = ("loss_grad" if want_grad else "loss_only") + ("_counts" if want_counts else "")
-    with torch.cuda.device(dev), _timed(tag, nbytes):
+    with torch.cuda.device(dev), _timed(tag, nbytes, main_kernel=True):
         if want_counts:
             rc = lib.robseg_loss_fwd_bwd_counts(*head, counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         else:
             rc = lib.robseg_loss_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_fwd_bwd")
-    _lib.count((2 if want_stats else 1) + (1 if want_counts else 0))
+    _lib.count((2 if want_stats else 1) + (2 if want_counts else 0))  # (+ counter zeroing and fold kernels)
     if want_stats:
         return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlogits, pred, loss_pix, counts)
     return LossOut(None, None, None, None, dlogits, pred, loss_pix, counts)
@@ -220,14 +240,14 @@ def loss_upsampled_fwd_bwd(low, labels, kind, weights=None, grad_scale=None, wan
             _ptr(fstat[0]) if want_stats else 0, _ptr(fstat[1]) if want_stats else 0,
             _ptr(istat[0]) if want_stats else 0, _ptr(istat[1]) if want_stats else 0)
     tag = ("loss_up_grad" if want_grad else "loss_up_only") + ("_counts" if want_counts else "")
-    with torch.cuda.device(dev), _timed(tag, nbytes):
+    with torch.cuda.device(dev), _timed(tag, nbytes, main_kernel=True):
         if want_counts:
             rc = lib.robseg_loss_upsampled_fwd_bwd_counts(*head, counts.data_ptr(), ws.data_ptr(), ws.numel(),
                                                           _stream())
         else:
             rc = lib.robseg_loss_upsampled_fwd_bwd(*head, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "robseg_loss_upsampled_fwd_bwd")
-    _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0) + (1 if want_counts else 0))
+    _lib.count(1 + (1 if want_grad else 0) + (1 if want_stats else 0) + (2 if want_counts else 0))
     if want_stats:
         return LossOut(fstat[0], fstat[1], istat[0], istat[1], dlow, pred, None, counts)
     return LossOut(None, None, None, None, dlow, pred, None, counts)
