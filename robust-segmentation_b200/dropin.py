@@ -205,6 +205,44 @@ def run_infer_main(argv, overrides=None):
     return ns
 
 
+_MISSING = object()
+
+
+def run_train_main(cfg, overrides=None, gpu=0, require_install=True):
+    """Run the reference's PIR-AT trainer -- ``Trainer(gpu, cfg)`` + ``Trainer.main()`` of ITS
+    ``tools/train_rob_seg.py`` (:63-145 model / DDP / loaders / optimiser, :270-352 the training loop with the
+    eval-mode inner attack, :353-440 periodic ``evaluate`` + checkpoints), unmodified -- in the rebound
+    ``tools.train_rob_seg`` namespace, i.e. with ``Pgd_Attack`` / ``attacker.apgd_train`` / ``evaluate`` /
+    ``get_loss`` being the B200 modules.  ``install()`` must have been called (the trainer binds these names when it
+    is imported; ``install`` rebinds them if that happened earlier).  ``overrides`` are extra names set in that
+    module for the duration of the run (tests swap ``get_segmentation_dataset`` for a synthetic dataset, and set
+    the reference's own classes back for the comparison run with ``require_install=False``).  The process group the
+    trainer creates (``setup_distributed``, world size = visible GPUs) is destroyed afterwards.  Returns the
+    ``Trainer`` (``save_path``, ``model``, ``optimizer``, ...)."""
+    if require_install and not _saved:
+        raise RuntimeError("dropin.install(reference_root) first")
+    import torch.distributed as dist
+
+    mod = importlib.import_module("tools.train_rob_seg")
+    saved = {}
+    for k, v in (overrides or {}).items():
+        saved[k] = getattr(mod, k, _MISSING)
+        setattr(mod, k, v)
+    trainer = None
+    try:
+        trainer = mod.Trainer(gpu=gpu, cfg=cfg)
+        trainer.main()
+        return trainer
+    finally:
+        for k, v in saved.items():
+            if v is _MISSING:
+                delattr(mod, k)
+            else:
+                setattr(mod, k, v)
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def fast_logit_upsample(model, head=False, fuse_loss=False):
     """Route the final logit up-sampling of a reference model through robseg's kernels.
 

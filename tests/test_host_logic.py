@@ -343,6 +343,12 @@ def test_dropin_on_the_real_reference_copy(mods, monkeypatch):
         TR = import_module("tools.train_rob_seg")
         assert TR.Pgd_Attack is mods.val.Pgd_Attack and TR.evaluate is mods.val.evaluate
         assert TR.attacker is mods.attacker and TR.get_loss is import_module("robseg_b200.semseg.losses").get_loss
+        # run_train_main reaches the reference's own Trainer (its __init__ reads cfg["TRAIN"] first) and puts the
+        # overridden names back whatever happens
+        theirs_ds, sentinel = TR.get_segmentation_dataset, object()
+        with pytest.raises(KeyError):
+            dropin.run_train_main({}, overrides={"get_segmentation_dataset": sentinel, "brand_new_name": 1})
+        assert TR.get_segmentation_dataset is theirs_ds and not hasattr(TR, "brand_new_name")
     finally:
         dropin.uninstall()
     for n, v in theirs.items():
@@ -350,6 +356,8 @@ def test_dropin_on_the_real_reference_copy(mods, monkeypatch):
     assert sys.modules["semseg.attacker"] is theirs["attacker"]
     with pytest.raises(RuntimeError):
         dropin.run_infer_main(["--help"])  # not installed any more
+    with pytest.raises(RuntimeError):
+        dropin.run_train_main({})
     _purge_reference_modules(monkeypatch)
 
 
