@@ -288,9 +288,13 @@ def variant_step(args, mods, dev, x, y, w, world, iters_per_step, fuse=False, gr
         if by:
             res["attack_side_ms_per_step"] = round(sum(by.values()), 3)
             res["kernels_ms_per_step"] = {k: round(v, 3) for k, v in by.items()}
-        res["what"] = ("one CUDA graph per APGD iteration (graphs.GraphedAttack: step + forward + loss + input-gradient "
-                       "backward + bookkeeping), the early-stop flag polled one iteration late" if graph else
-                       "robseg_loss_upsampled_fwd_bwd: the [B,C,512,512] logits / dlogits never exist")
+        what = []
+        if graph:
+            what.append("one CUDA graph per APGD iteration (graphs.GraphedAttack: step + forward + loss + input-gradient "
+                        "backward + bookkeeping), the early-stop flag polled one iteration late")
+        if fuse:
+            what.append("robseg_loss_upsampled_fwd_bwd: the [B,C,512,512] logits / dlogits never exist")
+        res["what"] = "; ".join(what)
         del model
         torch.cuda.empty_cache()
         return res
@@ -510,6 +514,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         line["config"]["fused_x4_variant"] = variant_step(args, mods, dev, x, y, w, world, iters_per_step, fuse=True)
         line["config"]["graph_variant"] = variant_step(args, mods, dev, x, y, w, world, iters_per_step, graph=True)
+        line["config"]["graph_fused_x4_variant"] = variant_step(args, mods, dev, x, y, w, world, iters_per_step,
+                                                                fuse=True, graph=True)
     if world == 1 and not args.no_ref_on_gpu:
         model = keep = keep_e2e = None
         torch.cuda.empty_cache()

@@ -193,8 +193,12 @@ def apgd_schedule(n_iter):
 def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss="ce", verbose=False,
                is_train=False, early_stop=False, track_loss=None, logger=None, y_target=None,
                ignore_index=-1, x_init=None, num_classes=21, weights=None, return_pred=False,
-               return_counts=False):
+               return_counts=False, gpuu=None):
     """APGD (L-inf) with the SEA losses; returns ``(x_best, acc, loss_best, x_best_adv)``.
+
+    ``gpuu`` is accepted and ignored: the reference trainer's APGD branch passes it
+    (tools/train_rob_seg.py:303-315) although the reference's own ``apgd_train`` does not take it
+    (that branch cannot run there; here it does, on the tensors' own device).
 
     ``return_pred=True`` (extension) appends ``pred_best``: the argmax map of
     ``x_best_adv`` as seen during the attack, which lets the SEA driver skip the re-forward of

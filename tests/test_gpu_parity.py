@@ -1043,6 +1043,31 @@ def test_pirat_training_step_flow(mods):
         assert torch.isfinite(loss) and float((adv - img).abs().max()) <= 4 / 255 + 1e-6
 
 
+def test_trainer_apgd_branch_call_runs(mods):
+    """The call of the reference trainer's APGD branch, verbatim (tools/train_rob_seg.py:303-315: loss="ce-avg",
+    track_loss=None, logger=None, gpuu=<gpu>).  The reference cannot execute it (its 2-argument "ce-avg" lambda is
+    called with 3 arguments and apgd_train has no ``gpuu``); the drop-in runs it, and ``gpuu`` changes
+    nothing."""
+    from functools import partial
+
+    C = 8
+    model = mods.consumers.TinySegNet(C, seed=2).to(dev()).eval()
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(3, 3, 32, 32, generator=g).to(dev())
+    lbl = torch.randint(0, C, (3, 32, 32), generator=g).to(dev())
+    attack_fn = partial(mods.attacker.apgd_train, norm="Linf", eps=4 / 255.0, n_iter=5, use_rs=True, loss="ce-avg",
+                        is_train=False, verbose=False, track_loss=None, logger=None, gpuu=0)
+    torch.manual_seed(7)
+    adv = attack_fn(model, img, lbl)[0]
+    torch.manual_seed(7)
+    plain = mods.attacker.apgd_train(model, img, lbl, "Linf", 4 / 255.0, n_iter=5, use_rs=True, loss="ce-avg")[0]
+    assert torch.equal(adv, plain)
+    assert float((adv - img).abs().max()) <= 4 / 255 + 1e-6 and float(adv.min()) >= 0 and float(adv.max()) <= 1
+    with torch.no_grad():
+        ce = torch.nn.functional.cross_entropy
+        assert float(ce(model(adv), lbl)) > float(ce(model(img), lbl))  # the attack raised the loss it maximises
+
+
 def test_custom_ops_registered(mods):
     mods.ops.register_custom_ops()
     z, y, w = make_problem(1, 21, 16, 16, 5)

@@ -221,7 +221,10 @@ def test_signature_parity_with_reference_surface(mods):
     assert list(sig.parameters)[:18] == ["model", "x", "y", "norm", "eps", "n_iter", "use_rs", "loss", "verbose",
                                          "is_train", "early_stop", "track_loss", "logger", "y_target",
                                          "ignore_index", "x_init", "num_classes", "weights"]
-    assert all(sig.parameters[k].default is False for k in list(sig.parameters)[18:])
+    ext = list(sig.parameters)[18:]
+    assert ext == ["return_pred", "return_counts", "gpuu"]
+    assert all(sig.parameters[k].default is False for k in ext[:2])
+    assert sig.parameters["gpuu"].default is None  # passed by tools/train_rob_seg.py:314, ignored
     assert set(a.criterion_dict) == {"ce", "ce-avg", "mask-ce-avg", "mask-ce-bal", "js-avg"}
     assert list(inspect.signature(a.compute_iou_acc).parameters) == [
         "pred", "target", "n_cls", "verbose", "ignore_index", "device"]
