@@ -739,9 +739,12 @@ static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C,
   const int wpb = warps_x < 8 ? warps_x : 8;  // warps per block (exact cover when <= 8)
   const int gx = (warps_x + wpb - 1) / wpb;
   int strip = h >= 128 ? 64 : 32;  // cell rows per thread strip: 2 halo block rows per strip
+  int bps = 16;                    // blocks per SM worth of (column group, strip) tiles; the rest is planes
+  if (const char* e = getenv("ROBSEG_UP_BWD_STRIP")) strip = atoi(e) > 0 ? atoi(e) : strip;
+  if (const char* e = getenv("ROBSEG_UP_BWD_BPS")) bps = atoi(e) > 0 ? atoi(e) : bps;
   if (strip > h) strip = h;
   const int gy = (h + strip - 1) / strip;
-  int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
+  int64_t gz = ((int64_t)sm_count() * bps + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
   gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
   if (gz > 65535) gz = 65535;
   const size_t ky_bytes = (size_t)(strip + 2) * ((3 * R + 3) & ~3) * sizeof(float);

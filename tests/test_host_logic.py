@@ -133,6 +133,39 @@ def test_bench_helpers():
     assert bench.upsample_mode(ns(stock_upsample=True)) is False
 
 
+def test_bench_roofline_assembly_and_traffic_provenance(monkeypatch):
+    """bench.sea_roofline: `achieved` over the loss kernel's OWN launches (the brackets the library records,
+    robseg_profile_next_kernel), the call-level brackets beside it; bench.load_traffic: the committed ncu capture is
+    passed on only for the kernel sources it was taken on."""
+    import bench
+
+    nb = 5066719232
+    by = {"loss_grad": [54 * nb, 54 * 0.8715, 54], "loss_grad_counts": [36 * nb, 36 * 0.881, 36], "apgd_step": [1, 1.0, 30]}
+    byk = {"loss_grad": [54 * nb, 54 * 0.8566, 54], "loss_grad_counts": [36 * nb, 36 * 0.8595, 36]}
+    r = bench.sea_roofline(by, byk, 16, 150, 512, (6454.6, "measured"), {"sm_mhz": 1965.0})
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["launches_timed"] == 90
+    assert abs(r["avg_launch_ms"] - (54 * 0.8566 + 36 * 0.8595) / 90) < 1e-4
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-4 and 0.91 < r["frac"] < 0.92
+    assert r["algorithmic_bytes_per_launch"] == nb
+    assert r["call_bracket"]["launches_timed"] == 54 and r["call_bracket_with_class_counters"]["launches_timed"] == 36
+    assert r["call_bracket"]["frac"] < r["kernel_uncounted"]["frac"]
+    # no kernel-level records (e.g. an older library): falls back to the call brackets and says so
+    r0 = bench.sea_roofline(by, {}, 16, 150, 512, (6454.6, "measured"), None)
+    assert r0["launches_timed"] == 90 and r0["timed_with"] == "events around the C call" and r0["frac"] < r["frac"]
+    # fused up-sampling route (SegMenter): the ex2-pipe fraction is reported beside the (by design small) HBM one
+    up = {"loss_up_grad": [13303808 * 10, 10 * 0.18, 10]}
+    ru = bench.sea_roofline(up, up, 4, 150, 512, (6454.6, "measured"), {"sm_mhz": 1965.0})
+    assert "ex2_pipe" in ru and ru["launches_timed"] == 10 and 0 < ru["ex2_pipe"]["frac"] < 1
+    # traffic: current capture -> value; other sources -> null + the stale value
+    v, cap = bench.load_traffic("sea_c150")
+    assert cap["kernel_source_sha"] == bench.kernel_source_sha() and cap["matches_tree"] and v > 4.9e9
+    assert cap["report"].endswith(".ncu-rep")
+    monkeypatch.setattr(bench, "kernel_source_sha", lambda: "0" * 16)
+    v2, cap2 = bench.load_traffic("sea_c150")
+    assert v2 is None and cap2["matches_tree"] is False and cap2["stale_value"] == v
+    assert bench.load_traffic("no_such_key") == (None, None)
+
+
 def test_exact_mean_matches_statistics_mean(mods):
     rng = np.random.default_rng(0)
     for _ in range(300):
