@@ -22,6 +22,18 @@ struct Tap {
   float w0, w1;
 };
 
+// Plane groups (gridDim.z) of the kernels whose blocks loop over planes p = z, z + gz, ...: at most `want`, and
+// then the smallest count that keeps the same number of loop trips, so every block runs ceil(planes / gz) or one
+// fewer planes.  (With gz = want the trip counts were e.g. 3 and 4 -- 8192 planes over 2368 groups -- and the
+// kernel's tail was a quarter of its duration; measured on the pow2 backward: 145 -> 117 us at 16x512x32^2 -> 128^2.)
+static inline unsigned plane_groups(int64_t want, int64_t planes) {
+  if (want < 1) want = 1;
+  if (want > planes) want = planes;
+  if (want > 65535) want = 65535;
+  const int64_t trips = (planes + want - 1) / want;
+  return (unsigned)((planes + trips - 1) / trips);
+}
+
 __device__ __forceinline__ Tap make_tap(int dst, float scale, int in_size) {
   float src = scale * ((float)dst + 0.5f) - 0.5f;
   src = src < 0.f ? 0.f : src;
@@ -153,8 +165,7 @@ static int launch_fwd_walk(const float* in, float* out, int64_t planes, int h, i
     if ((W + cand - 1) / cand * cand < (W + bs - 1) / bs * bs) bs = cand;
   const int gx = (W + bs - 1) / bs, gy = (H + kWalkStrip - 1) / kWalkStrip;
   int64_t gz = ((int64_t)sm_count() * 16 * (128 / bs) + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   upsample_fwd_walk_kernel<<<dim3(gx, gy, (unsigned)gz), bs, 0, stream>>>(in, out, planes, h, w, H, W, sy, sx);
   ROBSEG_LAUNCH_CHECK();
   return 0;
@@ -309,31 +320,51 @@ template <int R>
 __global__ void __launch_bounds__(128)
     upsample_fwd_pow2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes,
                              int h, int w) {
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  // CW output columns per thread, R / CW threads per input cell.  A thread that owned all 8 columns of an x8 cell
+  // wrote each output row with two 16-byte stores 32 bytes apart from its neighbour lane's: every store instruction
+  // filled half of each 32-byte sector it touched, twice the L2 transactions per byte (61 % of the roofline at
+  // 16x512x16^2 -> 128^2 against 81-90 % at x4).  With 4 columns per thread consecutive lanes write consecutive
+  // 16-byte pieces: one instruction = 512 contiguous bytes of an output row.
+  constexpr int CW = R < 4 ? R : 4, PARTS = R / CW;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cell = idx / PARTS, part = idx - cell * PARTS;
   if (cell >= h * w) return;
   const int a = cell / w, b = cell - a * w;
   const int H = R * h, W = R * w;
-  const WR<R> kx = make_wr<R>(b, w), ky = make_wr<R>(a, h);
+  const WR<R> ky = make_wr<R>(a, h);
+  float kx[CW][3];  // my CW columns of the cell's x-weights
+  {
+    const WR<R> all = make_wr<R>(b, w);
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = all.k[j][c];
+#pragma unroll
+        for (int q = 1; q < PARTS; ++q) v = part == q ? all.k[q * CW + j][c] : v;
+        kx[j][c] = v;
+      }
+  }
   const int cm = max(b - 1, 0), cp = min(b + 1, w - 1);
   const int rm = max(a - 1, 0), rp = min(a + 1, h - 1);
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
     const float* base = in + p * (int64_t)h * w;
-    float hx[3][R];
+    float hx[3][CW];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float* row = base + (int64_t)(r == 0 ? rm : (r == 1 ? a : rp)) * w;
       const float v0 = __ldg(row + cm), v1 = __ldg(row + b), v2 = __ldg(row + cp);
 #pragma unroll
-      for (int j = 0; j < R; ++j) hx[r][j] = kx.k[j][0] * v0 + kx.k[j][1] * v1 + kx.k[j][2] * v2;
+      for (int j = 0; j < CW; ++j) hx[r][j] = kx[j][0] * v0 + kx[j][1] * v1 + kx[j][2] * v2;
     }
-    float* o = out + (p * H + R * a) * (int64_t)W + R * b;
+    float* o = out + (p * H + R * a) * (int64_t)W + R * b + part * CW;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      float v[R];
+      float v[CW];
 #pragma unroll
-      for (int j = 0; j < R; ++j)
+      for (int j = 0; j < CW; ++j)
         v[j] = ky.k[i][0] * hx[0][j] + ky.k[i][1] * hx[1][j] + ky.k[i][2] * hx[2][j];
-      store_row<R>(o + (int64_t)i * W, v);
+      store_row<CW>(o + (int64_t)i * W, v);
     }
   }
 }
@@ -675,8 +706,7 @@ static int launch_bwd_walk(const float* gout, float* gin, int64_t planes, int C,
   if (strip > h) strip = h;
   const int gy = (h + strip - 1) / strip;
   int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   // rows per strip: (strip + 1) owners, each with <= ceil(1/sy) + 1 rows, plus the clamped rows
   const size_t rows_max = (size_t)((strip + 2) * (1.0 / sy + 1.0) + 8);
   const size_t smem = rows_max * sizeof(RowTap);
@@ -696,11 +726,10 @@ using namespace robseg;
 
 template <int R>
 static int launch_fwd_pow2(const float* in, float* out, int64_t planes, int h, int w, cudaStream_t stream) {
-  const int gx = (h * w + 127) / 128;
+  const int gx = (h * w * (R > 4 ? R / 4 : 1) + 127) / 128;  // R / 4 threads per cell beyond x4
   // ~32 resident blocks per SM worth of cell tiles; the rest of the parallelism is planes
   int64_t gz = ((int64_t)sm_count() * 32 + gx - 1) / gx;
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   upsample_fwd_pow2_kernel<R><<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(in, out, planes, h, w);
   ROBSEG_LAUNCH_CHECK();
   return 0;
@@ -711,8 +740,7 @@ static int launch_fwd_x2(const float* in, float* out, int64_t planes, int h, int
   const int gx = (cells + 127) / 128;
   // 72 registers -> 7 resident blocks per SM: two full waves of blocks, the rest of the planes in the block's loop
   int64_t gz = ((int64_t)sm_count() * 14 + gx - 1) / gx;
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   upsample_fwd_x2_kernel<<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(in, out, planes, h, w);
   ROBSEG_LAUNCH_CHECK();
   return 0;
@@ -723,8 +751,7 @@ static int launch_bwd_x2(const float* gout, float* gin, int64_t planes, int C, i
   const int cells = (h >> 1) * (w >> 1);
   const int gx = (cells + 127) / 128;
   int64_t gz = ((int64_t)sm_count() * 12 + gx - 1) / gx;  // two waves of 6 resident blocks per SM
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   upsample_bwd_x2_kernel<<<dim3(gx, 1, (unsigned)gz), 128, 0, stream>>>(gout, gin, planes, C, bs, cs, h, w);
   ROBSEG_LAUNCH_CHECK();
   return 0;
@@ -738,15 +765,22 @@ static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C,
   const int owned = (w + warps_x - 1) / warps_x;
   const int wpb = warps_x < 8 ? warps_x : 8;  // warps per block (exact cover when <= 8)
   const int gx = (warps_x + wpb - 1) / wpb;
-  int strip = h >= 128 ? 64 : 32;  // cell rows per thread strip: 2 halo block rows per strip
-  int bps = 16;                    // blocks per SM worth of (column group, strip) tiles; the rest is planes
+  // cell rows per thread strip (2 halo block rows per strip): 64 / 32 when there are planes enough to fill the
+  // GPU; with few planes the serial walk down a long strip is the critical path, so strips are halved until there
+  // are >= 8 tiles per SM (2x21x128^2 cells, the configs[0] logits: 49 -> 18 us at strip 8).  Plane groups: up to
+  // 64 blocks per SM worth of tiles, i.e. one plane per block up to ~9500 tiles -- the block loop over planes
+  // buys nothing here (the y-weight table is cheap) and its uneven trip counts cost 8-25 % (profiles/
+  // r02_kernel_brackets_and_trainer.md section 5).
+  int strip = h >= 128 ? 64 : 32;
+  int bps = 64;
+  if (strip > h) strip = h;
+  while (strip > 8 && (int64_t)gx * ((h + strip - 1) / strip) * planes < (int64_t)8 * sm_count()) strip >>= 1;
   if (const char* e = getenv("ROBSEG_UP_BWD_STRIP")) strip = atoi(e) > 0 ? atoi(e) : strip;
   if (const char* e = getenv("ROBSEG_UP_BWD_BPS")) bps = atoi(e) > 0 ? atoi(e) : bps;
   if (strip > h) strip = h;
   const int gy = (h + strip - 1) / strip;
   int64_t gz = ((int64_t)sm_count() * bps + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
-  gz = gz < 1 ? 1 : (gz > planes ? planes : gz);
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   const size_t ky_bytes = (size_t)(strip + 2) * ((3 * R + 3) & ~3) * sizeof(float);
   upsample_bwd_pow2_kernel<R><<<dim3(gx, gy, (unsigned)gz), 32 * wpb, ky_bytes, stream>>>(
       gout, gin, planes, C, bs, cs, h, w, strip, owned);
@@ -769,6 +803,9 @@ extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int
         return launch_fwd_pow2<2>(in, out, planes, h, w, stream);
       case 4: return launch_fwd_pow2<4>(in, out, planes, h, w, stream);
       case 8: return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
+      case 16:  // SegMenter's class masks (segmenter.py:228); ROBSEG_UP_FWD_QUAD=1: the generic quad kernel
+        if (!getenv("ROBSEG_UP_FWD_QUAD")) return launch_fwd_pow2<16>(in, out, planes, h, w, stream);
+        break;
       default: break;
     }
   }
@@ -781,9 +818,7 @@ extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int
   const int gx = (int)((quads + 127) / 128);
   // ~32 resident blocks per SM worth of quads; the rest of the parallelism is planes
   int64_t gz = ((int64_t)sm_count() * 32 + gx - 1) / gx;
-  if (gz < 1) gz = 1;
-  if (gz > planes) gz = planes;
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   dim3 grid((unsigned)gx, 1, (unsigned)gz);
   upsample_fwd_kernel<<<grid, 128, 0, stream>>>(in, out, planes, h, w, H, W, sy, sx);
   ROBSEG_LAUNCH_CHECK();
@@ -842,9 +877,7 @@ extern "C" int robseg_upsample_bilinear_bwd_strided(const float* gout, int64_t N
                                    (int)smem));
   const int gx = (w + TX - 1) / TX, gy = (h + TY - 1) / TY;
   int64_t gz = ((int64_t)sm_count() * 16 + (int64_t)gx * gy - 1) / ((int64_t)gx * gy);
-  if (gz < 1) gz = 1;
-  if (gz > planes) gz = planes;
-  if (gz > 65535) gz = 65535;
+  gz = plane_groups(gz, planes);
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
   upsample_bwd_kernel<<<grid, 256, smem, stream>>>(gout, gin, planes, C, bs, cs, h, w, H, W, sy, sx, TY,
                                                    TX, RY, RX, KY, KX);

@@ -28,17 +28,18 @@ def t(fn, inner):
     return statistics.median(ts)
 
 
-shapes = [(16, 150, 128, 512), (16, 512, 32, 128), (16, 512, 16, 128), (24, 21, 118, 472), (2, 21, 128, 512)]
+shapes = [(16, 150, 128, 512), (16, 512, 32, 128), (16, 512, 16, 128), (24, 21, 118, 472), (2, 21, 128, 512),
+          (2, 512, 32, 128), (2, 512, 16, 128), (4, 150, 128, 512), (16, 150, 32, 512), (16, 150, 64, 512)]
 for B, C, s, S in shapes:
     gup = torch.randn(B, C, S, S, device=dev, generator=g)
     nb = 4 * (gup.numel() + B * C * s * s)
     base = t(lambda: ops._upsample_bwd(gup, s, s), "upsample_bwd")
     print(f"[{B},{C},{S},{S}]->{s} ({nb/1e6:.0f} MB): default {base*1e3:6.1f} us {nb/base/1e6:5.0f} GB/s", flush=True)
-    for strip in (16, 32, 64, 128):
+    for strip in (8, 16, 32, 64):
         if strip > s:
             continue
         row = []
-        for bps in (8, 16, 24, 32):
+        for bps in (32, 48, 64, 96):
             os.environ["ROBSEG_UP_BWD_STRIP"], os.environ["ROBSEG_UP_BWD_BPS"] = str(strip), str(bps)
             ms = t(lambda: ops._upsample_bwd(gup, s, s), "upsample_bwd")
             row.append(f"bps{bps:2d} {ms*1e3:6.1f} us {nb/ms/1e6:5.0f}")

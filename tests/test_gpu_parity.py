@@ -726,7 +726,11 @@ def test_pgd_attack_vs_reference_run(mods, golden, tag, cls, los):
                                    (2, 5, 119, 119, 473, 473), (1, 3, 14, 14, 119, 119), (1, 3, 29, 29, 59, 59),
                                    (1, 2, 59, 60, 119, 121), (1, 2, 40, 70, 41, 71), (1, 2, 3, 100, 7, 333), (1, 1, 130, 5, 200, 9),
                                    # PSP pools of the head: 1, 2, 3, 6 -> 16
-                                   (1, 4, 1, 1, 16, 16), (1, 4, 2, 2, 16, 16), (1, 4, 3, 3, 16, 16), (1, 4, 6, 6, 16, 16)])
+                                   (1, 4, 1, 1, 16, 16), (1, 4, 2, 2, 16, 16), (1, 4, 3, 3, 16, 16), (1, 4, 6, 6, 16, 16),
+                                   # x16 (SegMenter's class masks) and x8 with two / four threads per input cell in the
+                                   # forward; few planes of tall images: the backward halves its row strips (64 -> 8)
+                                   (1, 2, 32, 32, 512, 512), (1, 3, 5, 7, 80, 112), (1, 2, 1, 3, 16, 48), (1, 3, 9, 33, 72, 264),
+                                   (1, 2, 128, 6, 512, 24), (1, 3, 130, 5, 520, 20), (1, 40, 32, 32, 128, 128)])
 def test_upsample_bilinear_vs_torch(mods, shape):
     """robseg_upsample_bilinear_fwd/_bwd vs F.interpolate(..., 'bilinear', align_corners=False) and
     its autograd backward; the backward is a gather, so repeated runs are bit-identical."""
