@@ -493,13 +493,16 @@ __global__ void __launch_bounds__(128, 6)
 template <int R>
 __global__ void __launch_bounds__(256)
     upsample_bwd_pow2_kernel(const float* __restrict__ gout, float* __restrict__ gin, int64_t planes,
-                             int C, int64_t bs, int64_t cs, int h, int w, int strip, int owned) {
+                             int C, int64_t bs, int64_t cs, int h, int w, int strip, int owned, int halo) {
   constexpr int G = R < 4 ? R : (R > 8 ? 2 : 4);  // output rows per prefetch group
   constexpr int KYS = (3 * R + 3) & ~3;       // padded floats of y-weights per cell row
   extern __shared__ __align__(16) float ky_tab[];  // [cell rows of the strip + halo][KYS]
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int b = gw * owned + lane - 1;  // lane 0 / owned+1: halo columns
+  // lane 0 / owned+1: halo columns (halo = 1).  A plane no wider than a warp needs none (halo = 0, lane = column):
+  // the columns left of 0 / right of w-1 do not exist and the border cells' weights towards them are exactly zero,
+  // so what the shuffles bring in from the unused lanes is multiplied out -- 32 of 32 lanes at w = 32 instead of 18.
+  const int b = gw * owned + lane - halo;
   const int a0 = blockIdx.y * strip, a1 = min(a0 + strip, h);
   const int a_first = max(a0 - 1, 0), a_last = min(a1, h - 1);
   // the y-weights depend only on the cell row: build them once per block
@@ -515,8 +518,8 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (gw * owned >= w) return;  // whole warp past the image
   const int64_t W = (int64_t)R * w;
-  const bool loads = b >= 0 && b < w && lane <= owned + 1;
-  const bool owns = loads && lane >= 1 && lane <= owned;
+  const bool loads = b >= 0 && b < w && lane <= owned + 2 * halo - 1;
+  const bool owns = loads && lane >= halo && lane < owned + halo;
   const int bcl = min(max(b, 0), w - 1);
   const WR<R> kx = make_wr<R>(bcl, w);  // transposed taps of my R outputs
   for (int64_t p = blockIdx.z; p < planes; p += gridDim.z) {
@@ -559,8 +562,10 @@ __global__ void __launch_bounds__(256)
             pc = fmaf(kx.k[j][1], v[i][j], pc);
             pr = fmaf(kx.k[j][2], v[i][j], pr);
           }
-          const float from_left = __shfl_up_sync(0xffffffffu, pr, 1);     // lane-1's share for my cell
-          const float from_right = __shfl_down_sync(0xffffffffu, pl, 1);  // lane+1's share for my cell
+          // lane-1's / lane+1's share for my cell (the shuffles hand lanes 0 / 31 their own value back: without
+          // halo lanes those two own cells, whose missing neighbour contributes nothing)
+          const float sl = __shfl_up_sync(0xffffffffu, pr, 1), sr = __shfl_down_sync(0xffffffffu, pl, 1);
+          const float from_left = lane > 0 ? sl : 0.f, from_right = lane < 31 ? sr : 0.f;
           const float xr = (from_left + pc) + from_right;
           const int r = g * G + i;
           acc_prev = fmaf(ky[3 * r], xr, acc_prev);
@@ -761,7 +766,8 @@ template <int R>
 static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C, int64_t bs, int64_t cs,
                            int h, int w, cudaStream_t stream) {
   // cells per warp: spread the columns evenly over the fewest warps (<= 30 owned + 2 halo lanes)
-  const int warps_x = (w + 29) / 30;
+  const int halo = (w <= 32 && !getenv("ROBSEG_UP_BWD_HALO")) ? 0 : 1;  // a warp that spans the plane needs no halo lanes
+  const int warps_x = halo ? (w + 29) / 30 : 1;
   const int owned = (w + warps_x - 1) / warps_x;
   const int wpb = warps_x < 8 ? warps_x : 8;  // warps per block (exact cover when <= 8)
   const int gx = (warps_x + wpb - 1) / wpb;
@@ -783,7 +789,7 @@ static int launch_bwd_pow2(const float* gout, float* gin, int64_t planes, int C,
   gz = plane_groups(gz, planes);
   const size_t ky_bytes = (size_t)(strip + 2) * ((3 * R + 3) & ~3) * sizeof(float);
   upsample_bwd_pow2_kernel<R><<<dim3(gx, gy, (unsigned)gz), 32 * wpb, ky_bytes, stream>>>(
-      gout, gin, planes, C, bs, cs, h, w, strip, owned);
+      gout, gin, planes, C, bs, cs, h, w, strip, owned, halo);
   ROBSEG_LAUNCH_CHECK();
   return 0;
 }
@@ -802,9 +808,13 @@ extern "C" int robseg_upsample_bilinear_fwd(const float* in, int64_t planes, int
           return launch_fwd_x2(in, out, planes, h, w, stream);
         return launch_fwd_pow2<2>(in, out, planes, h, w, stream);
       case 4: return launch_fwd_pow2<4>(in, out, planes, h, w, stream);
-      case 8: return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
+      // (planes of a few cells -- the head's 1x1 / 2x2 PSP pools -> 16x16 -- would leave most of a 128-thread
+      // block idle: they take the generic kernel below, whose threads are quads of the OUTPUT plane)
+      case 8:
+        if (h * w >= 32) return launch_fwd_pow2<8>(in, out, planes, h, w, stream);
+        break;
       case 16:  // SegMenter's class masks (segmenter.py:228); ROBSEG_UP_FWD_QUAD=1: the generic quad kernel
-        if (!getenv("ROBSEG_UP_FWD_QUAD")) return launch_fwd_pow2<16>(in, out, planes, h, w, stream);
+        if (h * w >= 32 && !getenv("ROBSEG_UP_FWD_QUAD")) return launch_fwd_pow2<16>(in, out, planes, h, w, stream);
         break;
       default: break;
     }
