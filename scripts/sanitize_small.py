@@ -39,7 +39,11 @@ for shp in [(1, 3, 8, 8, 32, 32), (1, 2, 7, 9, 28, 36), (1, 2, 5, 6, 13, 17), (1
             (1, 2, 6, 6, 16, 16), (1, 2, 33, 32, 66, 64), (1, 2, 30, 30, 119, 119), (1, 2, 14, 14, 119, 119),
             (1, 2, 59, 60, 119, 121), (1, 1, 70, 5, 100, 9),
             # exact x2 with even sides: the 2x2-cells-per-thread kernels (borders, one 2x2 plane, plane loop)
-            (2, 3, 16, 16, 32, 32), (1, 2, 6, 10, 12, 20), (3, 4, 2, 2, 4, 4), (1, 700, 4, 4, 8, 8)]:
+            (2, 3, 16, 16, 32, 32), (1, 2, 6, 10, 12, 20), (3, 4, 2, 2, 4, 4), (1, 700, 4, 4, 8, 8),
+            # x16 / x8 forward with four / two threads per cell, backward without halo lanes (w <= 32) and with
+            # halved strips (few planes of a tall image), w = 32 exactly (all 32 lanes own a column)
+            (1, 2, 8, 8, 128, 128), (1, 3, 5, 7, 80, 112), (1, 2, 130, 6, 520, 24), (1, 2, 9, 32, 36, 128),
+            (1, 2, 9, 33, 72, 264), (2, 2, 32, 32, 256, 256)]:
     a = torch.randn(*shp[:4], generator=g).to(dev).requires_grad_()
     o = ops.upsample_bilinear(a, shp[4:]); o.sum().backward()
 # gradient read in place from a channel slice of a concatenated gradient (strided planes)
