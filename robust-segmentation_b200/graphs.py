@@ -24,7 +24,39 @@ The parameters are constants of the attack: their ``requires_grad`` is switched 
 backward is captured so the graph holds only the input-gradient path (what
 ``torch.autograd.grad(loss, [x_adv])`` computes in the reference, attacker.py:350,469).
 """
+import contextlib
+import gc
+
 import torch
+
+
+# Capture with thread-local error checking: torch's default ("global") lets a CUDA call that is illegal during capture
+# -- cudaHostAlloc, cudaEventQuery, cudaFree -- from ANY thread of the process invalidate the capture in progress.
+# The attack is captured lazily, at the first batch of a loader loop, i.e. exactly while a DataLoader's pin-memory
+# thread (tools/infer.py builds its loaders with pin_memory=True), an NCCL watchdog or a garbage-collected object of
+# another thread may issue such calls; only this thread's own work goes into the graph, so only it is checked.
+_CAPTURE_MODE = "thread_local"
+
+
+@contextlib.contextmanager
+def _capturing(graph, pool=None):
+    """``torch.cuda.graph`` with the garbage collector out of the way.  Destroying a ``torch.cuda.CUDAGraph`` releases its
+    memory pool (cudaFree), which is illegal while a stream of the same thread is capturing and invalidates that
+    capture.  A dropped GraphedModel / GraphedAttack sits in a reference cycle, so its graphs die whenever the cyclic
+    collector happens to run -- in the middle of the next capture, if it is triggered there (seen on the B200 box:
+    'operation not permitted when stream is capturing (function reset)' five times, one per graph of the previous
+    model, then cudaErrorStreamCaptureInvalidated at capture_end; torch >= 2.10 no longer collects on entering
+    ``torch.cuda.graph`` unless torch.compiler.config.force_cudagraph_gc is set).  So: collect now, and keep the
+    collector off until the capture has ended."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, pool=pool, capture_error_mode=_CAPTURE_MODE):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class GraphedModel:
@@ -51,11 +83,11 @@ class GraphedModel:
                 del out
             cur.wait_stream(side)
             self.fwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.fwd):
+            with _capturing(self.fwd):
                 self.logits = model(self.x)
             self.gout = torch.zeros_like(self.logits)
             self.bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
+            with _capturing(self.bwd, pool=self.fwd.pool()):
                 (self.gx,) = torch.autograd.grad(self.logits, [self.x], grad_outputs=self.gout)
         finally:
             for p, r in zip(model.parameters(), req):
@@ -178,7 +210,7 @@ class GraphedAttack:
             g = {}
             for name, (with_step, with_grad) in (("init", (False, True)), ("it", (True, True)), ("last", (True, False))):
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, pool=self.pool):
+                with _capturing(graph, pool=self.pool):
                     out, track = self._body(kind, track_loss, with_step, with_grad)
                 if self.pool is None:
                     self.pool = graph.pool()

@@ -12,4 +12,4 @@ for n,v in k.items(): print('   %-70s %8.4f ms %8.1f GB/s %.3f %s' % (n[:70], v[
 import json; d=json.load(open('gpurun_out/r2f_bench_ref.json')); print('reference arm', d['value'], d['ms_per_step'], d['cpu_baseline']['cores'])"
 (timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err); python -c "
 import json; d=json.load(open('gpurun_out/r2f_bench.json')); c=d['config']; print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], [c.get(k,{}).get('value') for k in ('fused_x4_variant','graph_variant','graph_fused_x4_variant')], c['kernels_ms_per_step'], c['reference_on_gpu'].get('value'), d.get('cpu_baseline',{}).get('value'), c.get('loss_kernel_c151'), d['clocks']); print(json.dumps(d['roofline']))" || tail -5 gpurun_out/r2f_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 1 --warmup 3 --no-ref-on-gpu --no-cpu-baseline > gpurun_out/r2f_ncu_bench.log 2>&1; wc -l gpurun_out/r2f_launches.csv
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 3000 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 1 --warmup 1 --no-ref-on-gpu --no-cpu-baseline > gpurun_out/r2f_ncu_bench.log 2>&1; wc -l gpurun_out/r2f_launches.csv

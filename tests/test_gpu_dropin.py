@@ -310,6 +310,8 @@ def test_run_train_main_executes_the_reference_trainer(env, tmp_path, monkeypatc
     must agree, and so must the validation numbers of its ``evaluate`` calls."""
     n_cls, size, bs = 7, 64, 2
     monkeypatch.setattr(torch.cuda, "device_count", lambda: 1)  # Trainer: world size = visible GPUs
+    # importing the trainer sets cudnn.deterministic = True for the process (tools/train_rob_seg.py:35)
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", torch.backends.cudnn.deterministic)
     cfg = {"DEVICE": "cuda", "SAVE_DIR": str(tmp_path), "ADDENDUM": "t",
            "MODEL": {"NAME": "UperNetForSemanticSegmentation", "BACKBONE": "ConvNeXt-T_CVST", "PRETRAINED": None},
            "DATASET": {"NAME": "ADE20K", "ROOT": "unused", "IGNORE_LABEL": -1, "N_CLS": n_cls, "SEED": 0},
