@@ -166,6 +166,52 @@ def test_bench_roofline_assembly_and_traffic_provenance(monkeypatch):
     assert bench.load_traffic("no_such_key") == (None, None)
 
 
+def test_graph_capture_keeps_the_garbage_collector_out(pkg, monkeypatch):
+    """graphs._capturing: garbage is collected BEFORE the capture starts and the cyclic collector stays off until it has
+    ended (a CUDAGraph destroyed mid-capture releases its memory pool, which invalidates the capture), thread-local
+    capture mode, and the collector's state is restored whatever happens inside."""
+    import contextlib
+    import gc
+    from importlib import import_module
+
+    import torch
+
+    graphs = import_module("robseg_b200.graphs")
+    seen = {}
+
+    class Cycle:
+        def __init__(self):
+            self.me = self
+
+        def __del__(self):
+            seen["collected_before_capture"] = "inside" not in seen
+
+    @contextlib.contextmanager
+    def fake_graph(graph, pool=None, capture_error_mode="global"):
+        seen["mode"], seen["pool"] = capture_error_mode, pool
+        seen["inside"] = gc.isenabled()
+        yield
+
+    monkeypatch.setattr(torch.cuda, "graph", fake_graph)
+    Cycle()  # garbage in a reference cycle, like a dropped GraphedModel
+    assert gc.isenabled()
+    with graphs._capturing(object(), pool="P"):
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    assert seen == {"collected_before_capture": True, "mode": "thread_local", "pool": "P", "inside": False}
+    with pytest.raises(ZeroDivisionError):
+        with graphs._capturing(object()):
+            1 / 0
+    assert gc.isenabled()
+    gc.disable()  # a caller that runs with the collector off keeps it off
+    try:
+        with graphs._capturing(object()):
+            pass
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
+
+
 def test_exact_mean_matches_statistics_mean(mods):
     rng = np.random.default_rng(0)
     for _ in range(300):
