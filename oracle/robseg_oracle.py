@@ -454,7 +454,9 @@ def upsample_bilinear_bwd(g, h, w):
     Mx = np.zeros((W, w))
     np.add.at(Mx, (np.arange(W), x0), wx0.astype(np.float64))
     np.add.at(Mx, (np.arange(W), x1), wx1.astype(np.float64))
-    return np.einsum("Yy,...YX,Xx->...yx", My, g, Mx)
+    # two matrix products (x first, then y) instead of one three-operand einsum, which numpy evaluates as a single
+    # O(H W h w) loop nest per plane: 14 s for two 512 x 512 planes against 0.02 s
+    return np.matmul(My.T, np.matmul(g, Mx))
 
 
 class TorchModelAdapter:
