@@ -384,10 +384,13 @@ def test_run_train_main_executes_the_reference_trainer(env, tmp_path, monkeypatc
     # turns noise-level gradient differences into full-size steps, and the REFERENCE'S OWN trajectory changes from run to
     # run at the 1e-4 level by the third step (ATen's bilinear up-sampling backward accumulates with float atomics;
     # observed 2.50580 vs 2.50562 between two reference runs on the same box), so later steps are compared loosely.
+    # (observed over five runs on different boxes: steps 1-2 <= 4e-7, step 3 <= 1e-4, steps 4-6 <= 5e-3, any step <= 6 %,
+    # mean of the last ten <= 1 %; the bounds below leave a factor >= 4 on each)
     np.testing.assert_allclose(l1[:2], l2[:2], rtol=1e-5)
-    np.testing.assert_allclose(l1[:4], l2[:4], rtol=2e-3)
-    np.testing.assert_allclose(l1, l2, rtol=0.15)
-    assert abs(np.mean(l1[-10:]) - np.mean(l2[-10:])) <= 0.05 * np.mean(l2[-10:])
+    np.testing.assert_allclose(l1[2], l2[2], rtol=1e-3)
+    np.testing.assert_allclose(l1[:6], l2[:6], rtol=2e-2)
+    np.testing.assert_allclose(l1, l2, rtol=0.25)
+    assert abs(np.mean(l1[-10:]) - np.mean(l2[-10:])) <= 0.08 * np.mean(l2[-10:])
     assert np.mean(l1[-10:]) < 0.6 * l1[0]  # it trains
     assert len(evals["dropin"]) == len(evals["ref"]) == 2  # after iteration 40 and the final full pass
     assert evals["dropin"][0] == evals["dropin"][1] and evals["ref"][0] == evals["ref"][1]  # same weights, same metrics
@@ -404,5 +407,6 @@ def test_run_train_main_executes_the_reference_trainer(env, tmp_path, monkeypatc
     p2 = torch.cat([p.detach().flatten() for p in t2.model.parameters()])
     print("parameters after 40 steps: max |diff| %.3e, mean |diff| %.3e" % (float((p1 - p2).abs().max()),
                                                                              float((p1 - p2).abs().mean())))
-    # 40 AdamW steps at lr <= 1e-4 from the same initialisation: a single element can drift by 2 * steps * lr
-    assert float((p1 - p2).abs().max()) <= 1e-2 and float((p1 - p2).abs().mean()) <= 1e-3
+    # 40 AdamW steps at lr <= 1e-4 from the same initialisation: a single element can drift by 2 * steps * lr and more
+    # (Adam's first steps can be up to (1 - b1) / sqrt(1 - b2) = 3.2 x lr long on an element)
+    assert float((p1 - p2).abs().max()) <= 3e-2 and float((p1 - p2).abs().mean()) <= 2e-3
