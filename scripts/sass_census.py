@@ -44,5 +44,28 @@ for fn in order:
     print(f"| `{name}` | {total[fn]} | " + " | ".join(str(counts[fn].get(w, "")) for w in WATCH[:16]) + " |")
 tc = sum(counts[f][w] for f in order for w in ("UTC", "HMMA", "LDTM"))
 print(f"\ntensor-core / TMEM instructions in the library: {tc}")
-if "--excerpt" in sys.argv:
-    pass
+# excerpt: the producer warp's TMA issue of the SEA loss kernel (mbarrier expect-tx, UTMALDG) and a consumer wait
+target = next((f for f in order if demangle(f).startswith("void robseg::loss_tma_kernel<float, 2, 1, 0>")), None)
+if target:
+    body, on = [], False
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = m.group(1) == target
+            continue
+        if on and re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", line):
+            body.append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", line.rstrip()))
+    idx = [i for i, l in enumerate(body) if "UTMALDG" in l]
+    print(f"\n## Excerpt: `{demangle(target).split('(')[0]}` ({len(body)} SASS instructions)\n")
+    print("The producer warp arms the stage's mbarrier with the expected byte count (`SYNCS.ARRIVE.TRANS64` after `SYNCS.EXCH` "
+          "initialised it) and issues ONE 3-D tensor load per stage (`UTMALDG.3D`: a [C x 64-pixel] box of one image, issued by an "
+          "elected lane); `SYNCS.PHASECHK.TRANS64.TRYWAIT` is the mbarrier wait -- the producer's for a released stage before it "
+          "re-fills it (the first one below), the consumers' for the stage's bytes before their first shared-memory read.\n")
+    print("```")
+    for i in idx[:1]:
+        print("\n".join(body[max(0, i - 10):i + 4]))
+    waits = [i for i, l in enumerate(body) if "TRYWAIT" in l]
+    if waits:
+        print("        ...")
+        print("\n".join(body[max(0, waits[0] - 2):waits[0] + 3]))
+    print("```")
