@@ -20,6 +20,7 @@ and shadow the rebinding, so only the main block is compiled from the file's own
 """
 import ast
 import importlib
+import os
 import sys
 import types
 
@@ -241,6 +242,36 @@ def run_train_main(cfg, overrides=None, gpu=0, require_install=True):
                 setattr(mod, k, v)
         if dist.is_available() and dist.is_initialized():
             dist.destroy_process_group()
+
+
+def _train_worker(gpu, cfg, reference_root, shims):
+    """Body of one spawned trainer process: the rebinding lives in module state, so a fresh interpreter has to
+    install it again before ITS import of tools.train_rob_seg builds the Trainer."""
+    if reference_root is not None and os.getcwd() != reference_root:
+        os.chdir(reference_root)  # the reference opens ./configs/... relative to its checkout (semseg/utils/utils.py:259)
+    install(reference_root, shims=shims)
+    run_train_main(cfg, gpu=gpu)
+
+
+def launch_train(cfg, reference_root, world_size=None, shims=True):
+    """``Trainer.launch_from_args(world_size, cfg)`` (tools/train_rob_seg.py:455-462: one spawned process per GPU) with
+    the drop-in installed in every process.  ``torch.multiprocessing.spawn`` starts fresh interpreters, which import the
+    reference's modules unpatched -- calling the reference's own launcher after ``install()`` would therefore train on
+    the reference's attack in the children.  This launcher spawns ``__graft_entry__.dropin_train_worker`` instead (a
+    name a fresh interpreter can import: this package's directory name is not an identifier), which loads the package,
+    installs the drop-in and only then builds the reference's ``Trainer``.  ``world_size`` defaults to the visible GPUs
+    (the Trainer sizes its process group the same way, :76)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    ge = importlib.import_module("__graft_entry__")
+    n = torch.cuda.device_count() if world_size is None else int(world_size)
+    if n < 1:
+        raise RuntimeError("launch_train needs at least one CUDA device (no CPU fallback)")
+    mp.spawn(ge.dropin_train_worker, args=(cfg, reference_root, shims), nprocs=n, join=True)
 
 
 def fast_logit_upsample(model, head=False, fuse_loss=False):

@@ -443,6 +443,29 @@ def test_dropin_on_the_real_reference_copy(mods, monkeypatch):
     _purge_reference_modules(monkeypatch)
 
 
+def test_launch_train_installs_the_dropin_in_every_spawned_process(pkg):
+    """dropin.launch_train: torch.multiprocessing.spawn starts FRESH interpreters, so the rebinding has to be installed
+    inside each of them before the reference's Trainer is built (the reference's own launcher after install() would run
+    the reference's attack in its children).  One spawned process on the CPU: it must get as far as the reference's
+    Trainer.__init__ (which reads cfg["TRAIN"] first) with the B200 names bound -- the worker reports what it saw through
+    the exception it dies with."""
+    from importlib import import_module
+
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "semseg")):
+        pytest.skip("baseline/_ref not present")
+    dropin = import_module("robseg_b200.dropin")
+    import torch.multiprocessing as mp
+
+    with pytest.raises(mp.ProcessRaisedException) as ei:
+        dropin.launch_train({"probe": "dropin-names"}, ref, world_size=1)
+    msg = str(ei.value)
+    assert "KeyError" in msg and "TRAIN" in msg, msg[-800:]        # reached THEIR Trainer.__init__
+    assert "tools/train_rob_seg.py" in msg and "run_train_main" in msg  # ... through the installed drop-in
+    with pytest.raises(RuntimeError):
+        dropin.launch_train({}, ref, world_size=0)
+
+
 def test_run_sea_shards_the_loader_without_touching_foreign_batches(pkg):
     """a rank must only decode its own batches."""
     from importlib import import_module
