@@ -826,7 +826,11 @@ def load_traffic(key):
     v = d.get(key)
     if v is None:
         return None, None
-    sha, cur = d.get("_kernel_source_sha"), kernel_source_sha()
+    try:
+        cur = kernel_source_sha()
+    except OSError:  # sources not shipped with the library: provenance cannot be checked
+        cur = None
+    sha = d.get("_kernel_source_sha")
     cap = {"report": d.get("_reports", {}).get(key), "kernel_source_sha": sha, "matches_tree": sha == cur}
     if sha != cur:
         cap["stale_value"] = v
