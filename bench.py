@@ -12,6 +12,10 @@ bookkeeping: argmax of the adversarial points, exact int64 per-image counters, (
 int64 all-reduce), worst-case aACC.  ``value`` = attacked image-iterations per second over all
 ranks with the batch resident in HBM; ``e2e`` = the same through the public API with the batch
 coming from pinned host memory and x_adv / acc going back to the host every step.
+``roofline`` = the dominant robseg kernel of the step (loss_tma_kernel): algorithmic bytes per launch / its own average
+launch duration, from CUDA events the library records immediately before and after that launch on its stream
+(robseg_profile_next_kernel) for every loss+gradient launch of the timed steps; the wider brackets around the whole C
+call are reported beside it, ``traffic`` is the DRAM read+write of an ncu capture tied to the kernel-source sha.
 
 ``--impl reference`` times the CPU implementation of the same path on the box's host cores:
 the unmodified reference attacker when a copy travels under baseline/_ref, else the oracle port.
